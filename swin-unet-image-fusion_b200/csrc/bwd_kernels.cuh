@@ -1,0 +1,14 @@
+// Backward (gradient) implementations of the fused operators.
+#pragma once
+#include "common.cuh"
+
+namespace sf {
+size_t window_attn_bwd_ws(const sf_window_attn_bwd_params* p);
+int window_attn_bwd(const sf_window_attn_bwd_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t mlp_bwd_ws(const sf_mlp_bwd_params* p);
+int mlp_bwd(const sf_mlp_bwd_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t patch_bwd_ws(const sf_patch_bwd_params* p);
+int patch_bwd(const sf_patch_bwd_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t head_bwd_ws(const sf_head_bwd_params* p);
+int head_bwd(const sf_head_bwd_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace sf
