@@ -1,0 +1,135 @@
+"""bf16 tensor-core path (tcgen05): <= 2e-2 relative on the operator outputs and on the fused
+image (BASELINE.json north_star), against the reference-generated fixtures and the fp32 oracle."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import fusion_oracle as fo
+from oracle.make_golden import small_cfg
+from tests.util import TOL_BF16, build_model, dropin, golden, rel_err, rel_l2, wa_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(autouse=True)
+def _bf16_default():
+    sw = dropin()
+    sw.set_default_precision("bf16")
+    yield
+    sw.set_default_precision("fp32")
+
+
+@pytest.mark.parametrize("m,c,hidden", [(300, 24, 96), (1000, 48, 192), (257, 96, 384), (130, 192, 768), (128, 384, 1536),
+                                        (77, 24, 4), (500, 16, 40)])
+def test_fused_mlp_tcgen05(m, c, hidden):
+    sw = dropin()
+    g = torch.Generator().manual_seed(m + c)
+    x = torch.randn(1, c, 1, m, generator=g)
+    w1, b1 = torch.randn(hidden, c, 1, 1, generator=g) * (2 / c) ** 0.5, 0.1 * torch.randn(hidden, generator=g)
+    w2, b2 = torch.randn(c, hidden, 1, 1, generator=g) * (2 / hidden) ** 0.5, 0.1 * torch.randn(c, generator=g)
+    lg, lb = 1 + 0.2 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    nx = fo.layer_norm_c(x, lg, lb)
+    ref = x + torch.nn.functional.conv2d(torch.nn.functional.elu(torch.nn.functional.conv2d(nx, w1, b1)), w2, b2)
+    got = sw.ops.mlp(x.cuda(), w1=w1.cuda(), b1=b1.cuda(), w2=w2.cuda(), b2=b2.cuda(), ln=(lg.cuda(), lb.cuda()),
+                     residual=x.cuda(), precision="bf16")
+    assert rel_err(got, ref) <= TOL_BF16, rel_err(got, ref)
+    assert rel_l2(got, ref) <= 5e-3
+
+
+def test_window_attention_golden_cases_bf16():
+    dropin()
+    from a001_WindowAttention import WindowAttention
+    g, cases = wa_cases()
+    for c in cases:
+        t = c["tag"]
+        wa = WindowAttention(in_out_dims=c["c"], num_heads=c["nh"], dims_per_head=c["d"], window_size=(7, 7),
+                             use_cyclic_shift=c["shifted"], use_cross_attention=c["cross"], use_qkv_bias=True,
+                             attention_drop_ratio=0.0, linear_after_att_drop_ratio=0.0).eval()
+        wa.load_state_dict({k[len(t) + 3:]: T(g[k]) for k in g.files if k.startswith(t + "/p/")})
+        wa = wa.cuda()
+        q = T(g[t + "/q"]).cuda()
+        kv = T(g[t + "/kv"]).cuda() if c["cross"] else q
+        with torch.no_grad():
+            out = wa(q, kv, kv)
+        assert rel_err(out, T(g[t + "/out"])) <= TOL_BF16, (t, rel_err(out, T(g[t + "/out"])))
+
+
+@pytest.mark.parametrize("c,nh,d,hp,wp", [(24, 8, 3, 133, 133), (96, 8, 12, 35, 35), (192, 8, 24, 21, 21), (384, 8, 48, 14, 14)])
+def test_window_attention_model_shapes_bf16(c, nh, d, hp, wp):
+    sw = dropin()
+    g = torch.Generator().manual_seed(c)
+    x, y = torch.randn(2, c, hp, wp, generator=g), torch.randn(2, c, hp, wp, generator=g)
+    s = (1.0 / c) ** 0.5
+    p = {"q_for_heads.weight": torch.randn(nh * d, c, generator=g) * s, "q_for_heads.bias": torch.randn(nh * d, generator=g) * 0.1,
+         "k_for_heads.weight": torch.randn(nh * d, c, generator=g) * s, "k_for_heads.bias": torch.randn(nh * d, generator=g) * 0.1,
+         "v_for_heads.weight": torch.randn(nh * d, c, generator=g) * s, "v_for_heads.bias": torch.randn(nh * d, generator=g) * 0.1,
+         "linear_projection.weight": torch.randn(c, nh * d, generator=g) * s, "linear_projection.bias": torch.randn(c, generator=g) * 0.1,
+         "relative_position_bias_table": torch.randn(13, 13, generator=g)}
+    gx, bx = 1 + 0.2 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    gy, by = 1 + 0.2 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    cu = {k: v.cuda() for k, v in p.items()}
+    for shift, cross in ((False, False), (True, True)):
+        kv_ref = fo.layer_norm_c(y, gy, by) if cross else fo.layer_norm_c(x, gx, bx)
+        ref = x + fo.window_attention(fo.layer_norm_c(x, gx, bx), kv_ref, p, "", nh, d, (7, 7), shift)
+        got = sw.ops.window_attention(
+            x.cuda(), y.cuda() if cross else None, wq=cu["q_for_heads.weight"], bq=cu["q_for_heads.bias"],
+            wk=cu["k_for_heads.weight"], bk=cu["k_for_heads.bias"], wv=cu["v_for_heads.weight"], bv=cu["v_for_heads.bias"],
+            wo=cu["linear_projection.weight"], bo=cu["linear_projection.bias"], bias_table=cu["relative_position_bias_table"],
+            num_heads=nh, head_dim=d, window_size=(7, 7), shift=shift, ln_q=(gx.cuda(), bx.cuda()),
+            ln_kv=(gy.cuda(), by.cuda()) if cross else (gx.cuda(), bx.cuda()), residual=x.cuda(), precision="bf16")
+        assert rel_err(got, ref) <= TOL_BF16, (shift, cross, rel_err(got, ref))
+
+
+def test_patch_layers_bf16():
+    dropin()
+    from a010_StateRecorder import StateRecorder
+    from a011_PatchOperation import PatchMergingAndLinearLayer
+    g = golden("blocks_patch_pad.npz")
+    enc = PatchMergingAndLinearLayer(True, True, 6, 16, StateRecorder(), (2, 2), nn.ELU()).eval()
+    dec = PatchMergingAndLinearLayer(False, True, 16, 6, StateRecorder(), (2, 2), nn.ELU()).eval()
+    enc.load_state_dict({k[len("enc/p/"):]: T(g[k]) for k in g.files if k.startswith("enc/p/")})
+    dec.load_state_dict({k[len("dec/p/"):]: T(g[k]) for k in g.files if k.startswith("dec/p/")})
+    enc, dec = enc.cuda(), dec.cuda()
+    with torch.no_grad():
+        ex, ey = enc(T(g["enc/x"]).cuda(), T(g["enc/y"]).cuda())
+        dx, dy = dec(T(g["enc/ox"]).cuda(), T(g["enc/oy"]).cuda())
+    for got, key in ((ex, "enc/ox"), (ey, "enc/oy"), (dx, "dec/ox"), (dy, "dec/oy")):
+        assert rel_err(got, T(g[key])) <= TOL_BF16, (key, rel_err(got, T(g[key])))
+
+
+@pytest.mark.parametrize("tag,shape", [("b2_64", (2, 64, 64)), ("65x97", (1, 65, 97)), ("256", (1, 256, 256))])
+def test_default_model_bf16_against_reference_outputs(tag, shape):
+    g = golden("model_default.npz")
+    m = build_model().eval()
+    m.load_state_dict(fo.synth_state_dict(), strict=True)
+    ir, vis = fo.synth_inputs(*shape)
+    with torch.no_grad():
+        out = m(ir.cuda(), vis.cuda())
+    ref = T(g["out_" + tag])
+    e, l2 = rel_err(out, ref), rel_l2(out, ref)
+    print(f"bf16 model {tag}: rel_err {e:.3e} rel_l2 {l2:.3e}")
+    assert e <= TOL_BF16, (e, l2)
+
+
+def test_small_model_bf16():
+    g = golden("model_small.npz")
+    cfg = small_cfg()
+    m = build_model(cfg, act=nn.ELU()).eval()
+    m.load_state_dict(fo.synth_state_dict(cfg, seed=3), strict=True)
+    ir, vis = fo.synth_inputs(2, 37, 45, seed=5)
+    with torch.no_grad():
+        out = m(ir.cuda(), vis.cuda())
+    assert rel_err(out, T(g["out_eval"])) <= TOL_BF16
+
+
+def test_unsupported_shapes_raise_not_fallback():
+    sw = dropin()
+    x = torch.randn(1, 6, 7, 7, device="cuda")  # C % 4 != 0
+    with pytest.raises(sw.SwinFuseError):
+        sw.ops.mlp(x, w1=torch.randn(8, 6, 1, 1, device="cuda"), b1=torch.zeros(8, device="cuda"),
+                   w2=torch.randn(6, 8, 1, 1, device="cuda"), b2=torch.zeros(6, device="cuda"), precision="bf16")

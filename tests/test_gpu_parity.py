@@ -197,8 +197,15 @@ def test_stage_taps_against_oracle():
 
 
 def test_identical_modalities_raise_instead_of_exit():
-    m = build_model().eval()
-    x = torch.rand(1, 1, 32, 32, device="cuda")
+    """a005:111-118: a cross-attention block fed x == y prints and exit()s in the reference; the
+    drop-in raises instead."""
+    dropin()
+    from a005_BasicBlock import BasicBlock
+    blk = BasicBlock(in_out_dims=8, num_heads=2, dims_per_head=4, window_size=(7, 7), use_cyclic_shift=False,
+                     use_dual_path=True, use_cross_attr=True, use_qkv_bias=True, attention_drop_ratio=0.0,
+                     linear_after_att_drop_ratio=0.0, mlp_hidden_dims=16, mlp_activation_func=nn.ELU(),
+                     mlp_drop_ratio=0.0).cuda().eval()
+    x = torch.rand(1, 8, 7, 7, device="cuda")
     with pytest.raises(ValueError):
         with torch.no_grad():
-            m(x, x.clone())
+            blk(x, x.clone())
