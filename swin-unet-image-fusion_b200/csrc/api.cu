@@ -20,6 +20,16 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+const char* prof_name(const char* fmt, int v) {
+    static thread_local std::map<std::string, std::string>* pool = nullptr;
+    if (!pool) pool = new std::map<std::string, std::string>();
+    char buf[64];
+    snprintf(buf, sizeof(buf), fmt, v);
+    auto it = pool->find(buf);
+    if (it == pool->end()) it = pool->emplace(buf, buf).first;
+    return it->second.c_str();
+}
+
 struct ProfRecord { const char* name; double flops, bytes; cudaEvent_t e0, e1; };
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfRecord>* g_prof = nullptr;

@@ -1,12 +1,76 @@
-// bf16 tensor-core (tcgen05) implementations of the fused operators.
+// bf16 tensor-core (tcgen05) path: shared declarations.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace sf {
+using bf16 = __nv_bfloat16;
+
+static constexpr int TC_MAX_KPAD = 384;   // widest K whose A tile is kept resident in shared memory
+
+// ---- operator entry points (api.cu dispatches here for SF_PREC_BF16) ---------------------------
 size_t window_attn_ws_bf16(const sf_window_attn_params* p);
 int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t mlp_ws_bf16(const sf_mlp_params* p);
 int mlp_fwd_bf16(const sf_mlp_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t patch_ws_bf16(const sf_patch_params* p);
 int patch_fwd_bf16(const sf_patch_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// ---- weight packing (tc_gemm.cu) -------------------------------------------------------------------
+// Stacks up to 3 [Neach x K] fp32 matrices along N, splits rows into n_chunks of NR and columns
+// into k_chunks of KR, and writes for every (jn, jk) a bf16 UMMA operand image img[kc][r][8]
+// (= W[jn*NR + r][jk*KR + kc*8 + e], zero outside), images ordered jn-major; optional stacked,
+// zero-padded fp32 bias [n_chunks*NR].
+struct PackSrc { const float* w[3]; const float* b[3]; };
+int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
+                int k_chunks, cudaStream_t st);
+
+// ---- persistent token GEMM (tc_gemm.cu) ---------------------------------------------------------------
+enum { AM_F32 = 0, AM_F32_LN = 1, AM_TILED = 2, AM_MERGE = 3 };
+enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_TILED = 2 };
+
+struct TcGemm {
+    // ---- caller fills ----
+    const void* A;            // fp32 rows (AM_F32, AM_F32_LN), fp32 fine map (AM_MERGE), bf16 UMMA-tiled (AM_TILED)
+    long long M;
+    int K;
+    long long lda;            // elements (fp32 row modes)
+    int a_mode, out_mode;
+    const float* ln_g; const float* ln_b; float eps;
+    const bf16* Wp;           // packed weights: image [KS/8][NCH][8] per (n-chunk, k-slab)
+    int NCH, n_chunks;
+    const float* bias;        // [n_chunks*NCH] zero padded, or null
+    int elu;
+    int out_fp16;             // OUT_BF16 rows are written as IEEE fp16 instead of bf16
+    const float* residual; long long ldr;   // OUT_F32 only
+    void* out; long long ldo; int out_col0; int N;
+    int out_nkc;              // OUT_TILED: k-chunks per tile of the destination (= pad16(total columns)/8)
+    int Hf, Wf, Cin, mh, mw;  // AM_MERGE: fine map (B,Hf,Wf,Cin) and merging factors
+    // ---- tc_gemm_plan fills ----
+    int Kpad, KS, n_slabs, a_nkc, NA, NS, n_groups, chunks_per_group;
+};
+void tc_gemm_pick_nchunk(int Ntot, int* NCH, int* n_chunks);
+int tc_gemm_plan(TcGemm* p);          // needs K, a_mode, NCH, n_chunks, M
+int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st);
+
+// ---- fused small-channel MLP (tc_mlp.cu) -------------------------------------------------------------
+struct TcMlp {
+    const float* x; const float* residual; float* out;
+    long long M;
+    int C, Cpad, hidden, HC, n_hc;
+    const float* ln_g; const float* ln_b; float eps;
+    const bf16* W1p;   // n_hc images [Cpad/8][HC][8]   (rows = hidden chunk)
+    const bf16* W2p;   // n_hc images [HC/8][Cpad][8]   (rows = output channel, k = hidden chunk)
+    const float* b1;   // [n_hc*HC] zero padded
+    const float* b2;   // [C]
+};
+int tc_mlp_pick_hc(int Cpad, int hidden);
+int launch_tc_mlp(const TcMlp& t, cudaStream_t st);
+
+// ---- attention core (attn_core.cu) ----------------------------------------------------------------------
+// o_nkc == 0: O row-major [Mtok][ldo]; else O in the UMMA-tiled layout with o_nkc k-chunks per tile
+int launch_attn_core_bf16(const bf16* qkv, int qkv_fp16, long long ld, int koff, int voff, bf16* O, long long ldo, int o_nkc,
+                          const float* table, const WinGeom& g, int nh, int d, cudaStream_t st);
+
 }  // namespace sf

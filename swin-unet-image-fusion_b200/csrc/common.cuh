@@ -11,6 +11,8 @@ namespace sf {
 // ---- error / bookkeeping (thread local; never throws across the ABI) --------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// interned printf-style kernel label for ProfScope (stable pointer for the life of the process)
+const char* prof_name(const char* fmt, int v);
 
 // Optional per-kernel timing (sf_profile_enable): a ProfScope brackets the launches issued while
 // it is alive with a CUDA-event pair on the launching stream and books the algorithmic FLOPs /

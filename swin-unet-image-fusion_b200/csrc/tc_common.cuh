@@ -10,6 +10,7 @@
 // consumes two k-chunks; the descriptor start address advances by 2*LBO per K step.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace sf {
@@ -132,6 +133,10 @@ __host__ __device__ constexpr uint32_t lbo_padded(uint32_t rows) { return rows *
 __host__ __device__ constexpr uint32_t lbo_dense(uint32_t rows) { return rows * 16; }         // pre-packed weight images
 __host__ __device__ constexpr uint32_t pad16(uint32_t v) { return (v + 15) & ~15u; }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);

@@ -1,0 +1,583 @@
+// Persistent, warp-specialised tcgen05 token GEMM (sm_100a) and the weight packer.
+//
+//   out[M, N] = epilogue( prologue(A)[M, K] * W[N, K]^T )
+//
+// prologue: fp32 rows [-> LayerNorm] -> bf16 (written by 4 producer warps straight into the UMMA
+//           smem layout), patch-merge gather, or bf16 activations already stored in the UMMA-tiled
+//           layout in HBM (brought in by the bulk-copy engine, no thread touches them);
+// epilogue: + bias, ELU, + residual; fp32 rows, bf16 rows, or bf16 UMMA-tiled (the next GEMM's A).
+//
+// One CTA per SM (two when the tile is small) loops over work items (m-tile of 128 tokens x group
+// of n-chunks).  Warp roles:
+//   warps 0-3, 4-7  two A-producer groups, each filling its own A buffer (alternate work items, so two
+//                   tiles' global loads are in flight); idle in the STREAM flavour
+//   warp  8    MMA issuer         one lane issues tcgen05.mma, commits to mbarriers
+//   warp  9    loader             one lane drives cp.async.bulk for weight (and A) k-slabs
+//   warps 10-13 epilogue          tcgen05.ld -> registers -> global
+// Pipelines: A buffers (full/empty), k-slab ring (full/empty), two TMEM accumulators (full/empty),
+// so the producers work on item i+1 and the epilogue on chunk j-1 while the tensor core runs chunk j.
+#include <initializer_list>
+#include "bf16_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace sf {
+using namespace tc;
+
+static constexpr uint32_t SBO = 128;
+static constexpr int G_THREADS = 448;
+static constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+__host__ __device__ static inline uint32_t align128(uint32_t v) { return (v + 127) & ~127u; }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// =============================================================================================
+// weight packing
+// =============================================================================================
+__global__ void k_pack_w(PackSrc src, int nsrc, int Neach, int K, bf16* __restrict__ out, float* __restrict__ bias_out,
+                         int NR, int KR, int n_chunks, int k_chunks) {
+    const int Ntot = nsrc * Neach;
+    const long long cpi = (long long)NR * KR / 8;  // 16-byte chunks per image
+    const long long total = cpi * n_chunks * k_chunks;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        long long img = c / cpi;
+        int ci = (int)(c - img * cpi);
+        int jk = (int)(img % k_chunks), jn = (int)(img / k_chunks);
+        int kc = ci / NR, r = ci - kc * NR;
+        int n = jn * NR + r;
+        uint32_t pk[4] = {0, 0, 0, 0};
+        if (n < Ntot) {
+            int s = n / Neach;
+            const float* row = src.w[s] + (long long)(n - s * Neach) * K;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                int k = jk * KR + kc * 8 + e;
+                v[e] = k < K ? row[k] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+        }
+        *reinterpret_cast<uint4*>(out + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (bias_out) {
+        for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_chunks * NR; n += gridDim.x * blockDim.x) {
+            float b = 0.f;
+            if (n < Ntot) {
+                int s = n / Neach;
+                if (src.b[s]) b = src.b[s][n - s * Neach];
+            }
+            bias_out[n] = b;
+        }
+    }
+}
+
+int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
+                int k_chunks, cudaStream_t st) {
+    long long total = (long long)NR * KR / 8 * n_chunks * k_chunks;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    ProfScope ps("pack_weights_bf16", 0.0, 6.0 * (double)nsrc * Neach * K, st);
+    k_pack_w<<<blocks, 256, 0, st>>>(src, nsrc, Neach, K, out, bias_out, NR, KR, n_chunks, k_chunks);
+    SF_CHECK_LAUNCH("pack_weights_bf16");
+    return SF_OK;
+}
+
+// =============================================================================================
+// A producers (RESIDENT flavour): a [128 x Kpad] bf16 operand in the UMMA layout, LBO = 2064
+// =============================================================================================
+static constexpr uint32_t LBO_P = lbo_padded(128);  // producer-written A: 2064 B between k-chunks
+static constexpr uint32_t LBO_T = lbo_dense(128);   // bulk-copied (tiled) A: 2048 B
+
+// fp32 rows (optionally LayerNorm-ed) -> bf16.  Lanes of a warp split into groups of LPR lanes,
+// one group per row, NPER float4 per lane; RB row-iterations are loaded before any is processed
+// so that each lane keeps RB*NPER 16-byte loads in flight.
+template <bool LN, int NPER, int RB>
+__device__ __forceinline__ void produce_rows(uint8_t* sA, const float* __restrict__ A, long long lda, long long M, long long m0,
+                                             int K, int Kpad, const float* __restrict__ g, const float* __restrict__ b, float eps,
+                                             int ptid) {
+    const int lane = ptid & 31, warp = ptid >> 5;
+    const int nf4 = K >> 2, nslots = Kpad >> 2;
+    int LPR = 1;
+    while (LPR < 32 && LPR < nslots) LPR <<= 1;
+    const int RPW = 32 / LPR;
+    const int gl = lane & (LPR - 1), gr = lane / LPR;
+    const int iters = 32 / RPW;
+    for (int it0 = 0; it0 < iters; it0 += RB) {
+        float4 v[RB][NPER];
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const long long m = m0 + warp * 32 + (it0 + u) * RPW + gr;
+            const bool rowok = (it0 + u) < iters && m < M;
+#pragma unroll
+            for (int i = 0; i < NPER; i++) {
+                int q = gl + i * LPR;
+                v[u][i] = (rowok && q < nf4) ? *reinterpret_cast<const float4*>(A + m * lda + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            if (it0 + u >= iters) break;  // uniform
+            const int r = warp * 32 + (it0 + u) * RPW + gr;
+            const bool rowok = (m0 + r) < M;
+            if (LN) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < NPER; i++) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+                for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float mean = s / (float)K;
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < NPER; i++) {
+                    if (gl + i * LPR < nf4) {
+                        float dx = v[u][i].x - mean, dy = v[u][i].y - mean, dz = v[u][i].z - mean, dw = v[u][i].w - mean;
+                        ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                    }
+                }
+                for (int o = LPR >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                const float rstd = rsqrtf(ss / (float)K + eps);
+#pragma unroll
+                for (int i = 0; i < NPER; i++) {
+                    int q = gl + i * LPR;
+                    if (rowok && q < nf4) {
+                        float4 gg = __ldg(reinterpret_cast<const float4*>(g) + q), bb = __ldg(reinterpret_cast<const float4*>(b) + q);
+                        v[u][i].x = (v[u][i].x - mean) * rstd * gg.x + bb.x;
+                        v[u][i].y = (v[u][i].y - mean) * rstd * gg.y + bb.y;
+                        v[u][i].z = (v[u][i].z - mean) * rstd * gg.z + bb.z;
+                        v[u][i].w = (v[u][i].w - mean) * rstd * gg.w + bb.w;
+                    } else {
+                        v[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NPER; i++) {
+                int q = gl + i * LPR;
+                if (q < nslots) {
+                    uint2 pk = make_uint2(pack_bf16x2(v[u][i].x, v[u][i].y), pack_bf16x2(v[u][i].z, v[u][i].w));
+                    *reinterpret_cast<uint2*>(sA + (uint32_t)(q >> 1) * LBO_P + (uint32_t)r * 16 + (q & 1) * 8) = pk;
+                }
+            }
+        }
+    }
+}
+
+// Short rows (K <= 64): one thread per row, the whole row in registers -- no shuffles, the 32 rows
+// of a warp are independent instruction streams, st.shared of 16-byte chunks is conflict-free
+// (consecutive lanes = consecutive rows = consecutive 16 bytes).  A warp reads 32 consecutive rows,
+// i.e. one contiguous 32*K*4-byte span; the sectors a single LDG.128 half-uses are completed by the
+// next one out of L1.
+template <bool LN, int NF4MAX>
+__device__ __forceinline__ void produce_rows_thread(uint8_t* sA, const float* __restrict__ A, long long lda, long long M,
+                                                    long long m0, int K, int Kpad, const float* __restrict__ g,
+                                                    const float* __restrict__ b, float eps, int ptid) {
+    const int r = ptid;
+    const long long m = m0 + r;
+    const int nf4 = K >> 2, nkc = Kpad >> 3;
+    const bool rowok = m < M;
+    float4 v[NF4MAX];
+    const float4* src = reinterpret_cast<const float4*>(A + m * lda);
+#pragma unroll
+    for (int i = 0; i < NF4MAX; i++) v[i] = (rowok && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (LN) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NF4MAX; i++) { s0 += v[i].x + v[i].y; s1 += v[i].z + v[i].w; }
+        const float invk = 1.f / (float)K;
+        const float mean = (s0 + s1) * invk;
+        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NF4MAX; i++) {
+            if (i < nf4) {
+                float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                q0 += dx * dx + dy * dy; q1 += dz * dz + dw * dw;
+            }
+        }
+        const float rstd = rsqrtf((q0 + q1) * invk + eps);
+#pragma unroll
+        for (int i = 0; i < NF4MAX; i++) {
+            if (i < nf4) {
+                float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i), bb = __ldg(reinterpret_cast<const float4*>(b) + i);
+                v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
+                v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
+                v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
+                v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
+            }
+        }
+        if (!rowok) {
+#pragma unroll
+            for (int i = 0; i < NF4MAX; i++) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NF4MAX / 2; c++) {
+        if (c < nkc) {
+            uint4 pk = make_uint4(pack_bf16x2(v[2 * c].x, v[2 * c].y), pack_bf16x2(v[2 * c].z, v[2 * c].w),
+                                  pack_bf16x2(v[2 * c + 1].x, v[2 * c + 1].y), pack_bf16x2(v[2 * c + 1].z, v[2 * c + 1].w));
+            *reinterpret_cast<uint4*>(sA + (uint32_t)c * LBO_P + (uint32_t)r * 16) = pk;
+        }
+    }
+}
+
+template <bool LN>
+__device__ __forceinline__ void produce_a_f32(uint8_t* sA, const TcGemm& p, long long m0, int ptid) {
+    const float* A = reinterpret_cast<const float*>(p.A);
+    const int nslots = p.Kpad >> 2;
+    if (nslots <= 8) produce_rows_thread<LN, 8>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
+    else if (nslots <= 16) produce_rows_thread<LN, 16>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
+    else if (nslots <= 32) produce_rows<LN, 1, 8>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
+    else if (nslots <= 64) produce_rows<LN, 2, 4>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
+    else produce_rows<LN, 3, 4>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
+}
+
+// patch-merge gather (a011:87-93): row (b,Y,X), k = (ph*mw+pw)*Cin + c <- in[b][Y*mh+ph][X*mw+pw][c]
+__device__ __forceinline__ void produce_a_merge(uint8_t* sA, const TcGemm& p, long long m0, int ptid) {
+    const float* __restrict__ in = reinterpret_cast<const float*>(p.A);
+    const int nkc = p.Kpad >> 3;
+    const int Hc = p.Hf / p.mh, Wc = p.Wf / p.mw;
+    for (int idx = ptid; idx < 128 * nkc; idx += 128) {
+        int kc = idx >> 7, r = idx & 127;  // consecutive threads -> consecutive rows (conflict-free st.shared)
+        long long m = m0 + r;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = 0.f;
+        if (m < p.M) {
+            int X = (int)(m % Wc);
+            long long t = m / Wc;
+            int Y = (int)(t % Hc);
+            long long b = t / Hc;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                int k = kc * 8 + e;
+                if (k < p.K) {
+                    int q = k / p.Cin, c = k - q * p.Cin;
+                    int ph = q / p.mw, pw = q - ph * p.mw;
+                    v[e] = in[((b * p.Hf + (Y * p.mh + ph)) * p.Wf + (X * p.mw + pw)) * p.Cin + c];
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(sA + (uint32_t)kc * LBO_P + (uint32_t)r * 16) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
+// =============================================================================================
+// the kernel
+// =============================================================================================
+struct GemmSmem {
+    uint32_t a_bytes, a_off[2], w_off, stage_bytes, slabA_bytes, slabW_bytes, bar_off, total;
+};
+
+__host__ __device__ static inline GemmSmem gemm_smem_layout(const TcGemm& p) {
+    GemmSmem s{};
+    const bool stream = p.a_mode == AM_TILED;
+    s.a_bytes = stream ? 0u : align128((uint32_t)(p.Kpad >> 3) * LBO_P);
+    s.a_off[0] = 0;
+    s.a_off[1] = s.a_bytes;
+    s.w_off = (uint32_t)p.NA * s.a_bytes;
+    s.slabW_bytes = (uint32_t)p.NCH * (uint32_t)p.KS * 2u;
+    s.slabA_bytes = stream ? (uint32_t)(p.KS >> 3) * LBO_T : 0u;
+    s.stage_bytes = align128(s.slabW_bytes) + align128(s.slabA_bytes);
+    s.bar_off = s.w_off + (uint32_t)p.NS * s.stage_bytes;
+    s.total = s.bar_off + 256;
+    return s;
+}
+
+template <int AMODE, int OUTMODE>
+__global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr bool STREAM = (AMODE == AM_TILED);
+    const GemmSmem L = gemm_smem_layout(p);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* w_full = bars + 4;        // [NS <= 8]
+    uint64_t* w_empty = bars + 12;      // [NS <= 8]
+    uint64_t* d_full = bars + 20;       // [2]
+    uint64_t* d_empty = bars + 22;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    const uint32_t acc_stride = ((uint32_t)p.NCH + 31u) & ~31u;
+    const uint32_t ncols = tmem_cols_pow2(2u * acc_stride);
+    const int NS = p.NS, NA = p.NA, n_slabs = p.n_slabs, ksteps = p.KS >> 4;
+    const long long m_tiles = (p.M + 127) / 128;
+    const long long items = m_tiles * p.n_groups;
+
+    if (tid == 256) {  // warp 8 lane 0
+        for (int i = 0; i < 2; i++) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+        for (int i = 0; i < NS; i++) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, ncols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ------------------------------ A producers -------------------------------------------------
+        const uint32_t grp = (uint32_t)warp >> 2;
+        const int ptid = tid & 127;
+        if (!STREAM && (NA == 2 || grp == 0)) {
+            uint32_t acount = 0;
+            for (long long item = blockIdx.x; item < items; item += gridDim.x, acount++) {
+                const long long tile = item / p.n_groups;
+                const uint32_t ab = acount % (uint32_t)NA;
+                if (NA == 2 && ab != grp) continue;
+                mbar_wait(&a_empty[ab], ((acount / (uint32_t)NA) & 1u) ^ 1u);
+                uint8_t* sA = smem + L.a_off[ab];
+                if (AMODE == AM_F32_LN) produce_a_f32<true>(sA, p, tile * 128, ptid);
+                else if (AMODE == AM_F32) produce_a_f32<false>(sA, p, tile * 128, ptid);
+                else produce_a_merge(sA, p, tile * 128, ptid);
+                fence_async_smem();
+                mbar_arrive(&a_full[ab]);
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------ MMA issuer ----------------------------------------------------
+        if (lane == 0) {
+            uint32_t acount = 0, wit = 0, tcount = 0;
+            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.NCH);
+            const uint32_t lbo_w = lbo_dense((uint32_t)p.NCH);
+            const uint32_t lbo_a = STREAM ? LBO_T : LBO_P;
+            for (long long item = blockIdx.x; item < items; item += gridDim.x, acount++) {
+                const int group = (int)(item % p.n_groups);
+                const uint32_t ab = acount % (uint32_t)NA;
+                if (!STREAM) {
+                    mbar_wait(&a_full[ab], (acount / (uint32_t)NA) & 1u);
+                    tc_fence_after_sync();
+                }
+                const int c0 = group * p.chunks_per_group;
+                const int c1 = min(c0 + p.chunks_per_group, p.n_chunks);
+                for (int c = c0; c < c1; c++, tcount++) {
+                    const uint32_t acc = tcount & 1u;
+                    mbar_wait(&d_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
+                    tc_fence_after_sync();
+                    const uint32_t tacc = tmem_base + acc * acc_stride;
+                    for (int s = 0; s < n_slabs; s++, wit++) {
+                        const uint32_t stg = wit % (uint32_t)NS;
+                        mbar_wait(&w_full[stg], (wit / (uint32_t)NS) & 1u);
+                        tc_fence_after_sync();
+                        const uint32_t wbase = smem_u32(smem + L.w_off + stg * L.stage_bytes);
+                        const uint32_t abase = STREAM ? wbase + align128(L.slabW_bytes)
+                                                      : smem_u32(smem + L.a_off[ab]) + (uint32_t)s * (uint32_t)(p.KS >> 3) * lbo_a;
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            uint64_t da = make_smem_desc(abase + (uint32_t)ks * 2u * lbo_a, lbo_a, SBO);
+                            uint64_t db = make_smem_desc(wbase + (uint32_t)ks * 2u * lbo_w, lbo_w, SBO);
+                            umma_bf16(tacc, da, db, idesc, (s | ks) != 0);
+                        }
+                        umma_commit(&w_empty[stg]);
+                    }
+                    umma_commit(&d_full[acc]);
+                }
+                if (!STREAM) umma_commit(&a_empty[ab]);
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------ loader (bulk-copy engine) --------------------------------------
+        if (lane == 0) {
+            uint32_t wit = 0;
+            for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+                const long long tile = item / p.n_groups;
+                const int group = (int)(item % p.n_groups);
+                const int c0 = group * p.chunks_per_group;
+                const int c1 = min(c0 + p.chunks_per_group, p.n_chunks);
+                for (int c = c0; c < c1; c++) {
+                    for (int s = 0; s < n_slabs; s++, wit++) {
+                        const uint32_t stg = wit % (uint32_t)NS;
+                        mbar_wait(&w_empty[stg], ((wit / (uint32_t)NS) & 1u) ^ 1u);
+                        uint8_t* dstW = smem + L.w_off + stg * L.stage_bytes;
+                        mbar_arrive_expect_tx(&w_full[stg], L.slabW_bytes + L.slabA_bytes);
+                        bulk_g2s(dstW, p.Wp + ((size_t)c * n_slabs + s) * (size_t)p.NCH * p.KS, L.slabW_bytes, &w_full[stg]);
+                        if (STREAM) {
+                            const bf16* srcA = reinterpret_cast<const bf16*>(p.A) + ((size_t)tile * p.a_nkc + (size_t)s * (p.KS >> 3)) * 128 * 8;
+                            bulk_g2s(dstW + align128(L.slabW_bytes), srcA, L.slabA_bytes, &w_full[stg]);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------ epilogue ---------------------------------------------------------
+        const int rb = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = rb * 32 + lane;
+        uint32_t tcount = 0;
+        for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+            const long long tile = item / p.n_groups;
+            const int group = (int)(item % p.n_groups);
+            const long long m = tile * 128 + row;
+            const int c0 = group * p.chunks_per_group;
+            const int c1 = min(c0 + p.chunks_per_group, p.n_chunks);
+            for (int c = c0; c < c1; c++, tcount++) {
+                const uint32_t acc = tcount & 1u;
+                mbar_wait(&d_full[acc], (tcount >> 1) & 1u);
+                __syncwarp();
+                tc_fence_after_sync();
+                const uint32_t tlane = tmem_base + acc * acc_stride + ((uint32_t)(rb * 32) << 16);
+                const int ncol0 = c * p.NCH;
+                for (int c16 = 0; c16 < p.NCH; c16 += 16) {
+                    const int n0 = ncol0 + c16;
+                    if (n0 >= p.N) break;  // uniform
+                    float v[16];
+                    tmem_ld16(tlane + (uint32_t)c16, v);
+                    if (m < p.M) {
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                                v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+                            }
+                        }
+                        if (p.elu) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;
+                        }
+                        if (OUTMODE == OUT_TILED) {
+                            // chunk (tile, kc, r) at ((tile*out_nkc + kc)*128 + r)*8 elements; columns >= N are zero
+                            // (zero weights, zero bias, ELU(0) = 0) which is exactly the K padding the next GEMM needs
+                            bf16* o = reinterpret_cast<bf16*>(p.out);
+                            const int kc = (p.out_col0 + n0) >> 3;
+                            uint4 lo = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                            uint4 hi = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                            *reinterpret_cast<uint4*>(o + (((size_t)tile * p.out_nkc + kc) * 128 + row) * 8) = lo;
+                            if (kc + 1 < p.out_nkc) *reinterpret_cast<uint4*>(o + (((size_t)tile * p.out_nkc + kc + 1) * 128 + row) * 8) = hi;
+                        } else if (OUTMODE == OUT_BF16) {
+                            // 16-bit rows: bf16, or fp16 (out_fp16) for q/k/v whose consumer is the fp32 softmax
+                            // kernel, not the tensor core -- 3 more mantissa bits on the attention scores
+                            bf16* o = reinterpret_cast<bf16*>(p.out) + m * p.ldo + p.out_col0 + n0;
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) pk[i] = p.out_fp16 ? pack_f16x2(v[2 * i], v[2 * i + 1]) : pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                            if (n0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                                reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            } else {
+                                const uint16_t* h = reinterpret_cast<const uint16_t*>(pk);
+                                uint16_t* o16 = reinterpret_cast<uint16_t*>(o);
+#pragma unroll
+                                for (int i = 0; i < 16; i++) if (n0 + i < p.N) o16[i] = h[i];
+                            }
+                        } else {
+                            float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + p.out_col0 + n0;
+                            const float* rs = p.residual ? p.residual + m * p.ldr + n0 : nullptr;
+                            const bool vec = ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                if (vec && n0 + i + 4 <= p.N) {
+                                    float4 t = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                    if (rs) {
+                                        float4 rr = *reinterpret_cast<const float4*>(rs + i);
+                                        t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+                                    }
+                                    *reinterpret_cast<float4*>(o + i) = t;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; e++)
+                                        if (n0 + i + e < p.N) o[i + e] = v[i + e] + (rs ? rs[i + e] : 0.f);
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[acc]);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, ncols);
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+// k-slab width: the largest of {64, 48, 32, 16} dividing Kpad
+static int pick_ks(int Kpad) {
+    for (int ks : {64, 48, 32, 16})
+        if (Kpad % ks == 0) return ks;
+    return 16;
+}
+
+// chunk width along N (<= 256 so that two accumulators fit the 512 TMEM columns), balanced
+void tc_gemm_pick_nchunk(int Ntot, int* NCH, int* n_chunks) {
+    int npad = (int)pad16((uint32_t)Ntot);
+    int nc = (npad + 255) / 256;
+    *NCH = (int)pad16((uint32_t)((npad + nc - 1) / nc));
+    *n_chunks = nc;
+}
+
+int tc_gemm_plan(TcGemm* p) {
+    p->Kpad = (int)pad16((uint32_t)p->K);
+    p->KS = pick_ks(p->Kpad);
+    p->n_slabs = p->Kpad / p->KS;
+    const bool stream = p->a_mode == AM_TILED;
+    SF_CHECK_ARG(p->NCH % 16 == 0 && p->NCH >= 16 && p->NCH <= 256, "tc_gemm: bad n-chunk %d", p->NCH);
+    if (!stream) {
+        SF_CHECK_ARG(p->Kpad <= TC_MAX_KPAD, "tc_gemm: K=%d exceeds the resident-A limit %d", p->K, TC_MAX_KPAD);
+        if (p->a_mode != AM_MERGE) SF_CHECK_ARG(p->K % 4 == 0 && p->lda % 4 == 0, "tc_gemm: fp32 A needs K %% 4 == 0 (K=%d)", p->K);
+    } else {
+        p->a_nkc = p->Kpad >> 3;
+    }
+    const long long m_tiles = (p->M + 127) / 128;
+    // spread the n-chunks of one m-tile over several CTAs only when there are too few m-tiles
+    int groups = 1;
+    if (m_tiles < 296 && p->n_chunks > 1) {
+        groups = (int)((296 + m_tiles - 1) / m_tiles);
+        if (groups > p->n_chunks) groups = p->n_chunks;
+    }
+    p->chunks_per_group = (p->n_chunks + groups - 1) / groups;
+    p->n_groups = (p->n_chunks + p->chunks_per_group - 1) / p->chunks_per_group;
+    // shared memory: A buffers + k-slab ring
+    p->NA = stream ? 0 : 2;
+    p->NS = 4;
+    for (;;) {
+        GemmSmem L = gemm_smem_layout(*p);
+        if (L.total <= SMEM_LIMIT) break;
+        if (p->NS > 2) p->NS--;
+        else if (p->NA > 1) { p->NA = 1; p->NS = 4; }
+        else { set_error("tc_gemm: tile does not fit shared memory (K=%d, chunk=%d)", p->K, p->NCH); return SF_ERR_UNSUPPORTED; }
+    }
+    return SF_OK;
+}
+
+template <int AMODE, int OUTMODE>
+static int launch_t(const TcGemm& p, const char* name, cudaStream_t st) {
+    GemmSmem L = gemm_smem_layout(p);
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm2<AMODE, OUTMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        if (e != cudaSuccess) { set_error("tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
+        configured = true;
+    }
+    const long long m_tiles = (p.M + 127) / 128;
+    const long long items = m_tiles * p.n_groups;
+    const uint32_t ncols = tmem_cols_pow2(2u * (((uint32_t)p.NCH + 31u) & ~31u));
+    int per_sm = (L.total * 2 + 2048 <= SMEM_LIMIT && ncols <= 256) ? 2 : 1;
+    long long grid = 148LL * per_sm;
+    if (grid > items) grid = items;
+    const double abytes = (AMODE == AM_TILED ? 2.0 : 4.0) * (double)p.M * p.K;
+    const double obytes = (OUTMODE == OUT_F32 ? 4.0 : 2.0) * (double)p.M * p.N + (p.residual ? 4.0 * (double)p.M * p.N : 0.0);
+    ProfScope ps(name, 2.0 * (double)p.M * p.N * p.K, abytes + obytes + 2.0 * (double)p.N * p.K, st);
+    k_tc_gemm2<AMODE, OUTMODE><<<(unsigned)grid, G_THREADS, L.total, st>>>(p);
+    SF_CHECK_LAUNCH("tc_gemm");
+    return SF_OK;
+}
+
+int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st) {
+    if (p.a_mode == AM_F32_LN && p.out_mode == OUT_BF16) return launch_t<AM_F32_LN, OUT_BF16>(p, name, st);
+    if (p.a_mode == AM_F32 && p.out_mode == OUT_BF16) return launch_t<AM_F32, OUT_BF16>(p, name, st);
+    if (p.a_mode == AM_F32_LN && p.out_mode == OUT_TILED) return launch_t<AM_F32_LN, OUT_TILED>(p, name, st);
+    if (p.a_mode == AM_F32 && p.out_mode == OUT_TILED) return launch_t<AM_F32, OUT_TILED>(p, name, st);
+    if (p.a_mode == AM_TILED && p.out_mode == OUT_F32) return launch_t<AM_TILED, OUT_F32>(p, name, st);
+    if (p.a_mode == AM_F32 && p.out_mode == OUT_F32) return launch_t<AM_F32, OUT_F32>(p, name, st);
+    if (p.a_mode == AM_MERGE && p.out_mode == OUT_F32) return launch_t<AM_MERGE, OUT_F32>(p, name, st);
+    set_error("tc_gemm: unsupported mode combination (%d -> %d)", p.a_mode, p.out_mode);
+    return SF_ERR_INVALID;
+}
+
+}  // namespace sf
