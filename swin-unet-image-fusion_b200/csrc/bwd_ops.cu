@@ -1,12 +1,773 @@
-// Backward kernels -- placeholder: every entry reports SF_ERR_UNSUPPORTED.
+// Backward (gradient) kernels of the fused operators -- row a18 of SURVEY.md section 8.  The
+// reference defines no custom backward (pure autograd, a016:164); these kernels restate the
+// adjoints of a001/a003/a004/a011/a013 and are checked against autograd over the oracle.
+//
+// Every backward recomputes the forward intermediates from the operator inputs in fp32 (nothing
+// but the inputs is saved by the forward pass).  Weight / bias / table gradients are ACCUMULATED
+// into caller-zeroed buffers with fp32 atomics; activation gradients are written.
 #include "bwd_kernels.cuh"
+#include "fp32_kernels.cuh"
+
 namespace sf {
-size_t window_attn_bwd_ws(const sf_window_attn_bwd_params*) { return 0; }
-int window_attn_bwd(const sf_window_attn_bwd_params*, void*, size_t, cudaStream_t) { set_error("window attention backward is not built"); return SF_ERR_UNSUPPORTED; }
-size_t mlp_bwd_ws(const sf_mlp_bwd_params*) { return 0; }
-int mlp_bwd(const sf_mlp_bwd_params*, void*, size_t, cudaStream_t) { set_error("MLP backward is not built"); return SF_ERR_UNSUPPORTED; }
-size_t patch_bwd_ws(const sf_patch_bwd_params*) { return 0; }
-int patch_bwd(const sf_patch_bwd_params*, void*, size_t, cudaStream_t) { set_error("patch layer backward is not built"); return SF_ERR_UNSUPPORTED; }
-size_t head_bwd_ws(const sf_head_bwd_params*) { return 0; }
-int head_bwd(const sf_head_bwd_params*, void*, size_t, cudaStream_t) { set_error("head backward is not built"); return SF_ERR_UNSUPPORTED; }
+
+__device__ __forceinline__ float elu_grad(float pre) { return pre > 0.f ? 1.f : expf(pre); }
+
+// =============================================================================================
+// C[M,N] (+)= (A[M,K] * B[K,N]) (* ELU'(aux[M,N]))          B row-major [K][N]
+// =============================================================================================
+template <bool ACCUM, bool ELUAUX>
+__global__ void __launch_bounds__(256) k_gemm_nn(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ aux,
+                                                 float* __restrict__ C, long long M, int N, int K) {
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        {   // A tile: 64 rows x 16 k, thread -> (row = tid/4, 4 consecutive k)
+            const int lrow = tid >> 2, lk = (tid & 3) * 4;
+            const long long m = m0 + lrow;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int k = k0 + lk + e;
+                As[lk + e][lrow] = (m < M && k < K) ? A[m * K + k] : 0.f;
+            }
+        }
+        {   // B tile: 16 k x 64 n, thread -> (k = tid/16, 4 consecutive n)
+            const int lk = tid >> 4, ln = (tid & 15) * 4;
+            const int k = k0 + lk;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int n = n0 + ln + e;
+                Bs[lk][ln + e] = (k < K && n < N) ? B[(long long)k * N + n] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (ELUAUX) v *= elu_grad(aux[m * N + n]);
+            if (ACCUM) v += C[m * N + n];
+            C[m * N + n] = v;
+        }
+    }
+}
+
+static int launch_gemm_nn(const float* A, const float* B, const float* aux, float* C, long long M, int N, int K, bool accum,
+                          cudaStream_t st) {
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+    ProfScope ps("bwd_gemm_nn_f32", 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)M * N * (accum ? 2 : 1) + (double)K * N), st);
+    if (aux) {
+        if (accum) k_gemm_nn<true, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+        else k_gemm_nn<false, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+    } else {
+        if (accum) k_gemm_nn<true, false><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+        else k_gemm_nn<false, false><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+    }
+    SF_CHECK_LAUNCH("bwd_gemm_nn");
+    return SF_OK;
+}
+
+// =============================================================================================
+// Wg[N,K] += G[M,N]^T * f(A[M,K])      (f = identity or ELU); reduction over M split across CTAs
+// =============================================================================================
+template <bool ELU_A>
+__global__ void __launch_bounds__(256) k_gemm_tn_reduce(const float* __restrict__ G, const float* __restrict__ A, float* __restrict__ Wg,
+                                                        long long M, int N, int K, long long rows_per_split) {
+    __shared__ __align__(16) float Gs[16][64 + 4];
+    __shared__ __align__(16) float As[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const long long r0 = (long long)blockIdx.z * rows_per_split;
+    const long long r1 = min(M, r0 + rows_per_split);
+    float acc[4][4] = {};
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    for (long long r = r0; r < r1; r += 16) {
+        const long long m = r + lr;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            int n = n0 + lc + e, k = k0 + lc + e;
+            Gs[lr][lc + e] = (m < r1 && n < N) ? G[m * N + n] : 0.f;
+            float a = (m < r1 && k < K) ? A[m * K + k] : 0.f;
+            As[lr][lc + e] = ELU_A ? elu1(a) : a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+            float4 g = *reinterpret_cast<const float4*>(&Gs[rr][ty * 4]);
+            float4 a = *reinterpret_cast<const float4*>(&As[rr][tx * 4]);
+            float gv[4] = {g.x, g.y, g.z, g.w}, av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(gv[i], av[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + tx * 4 + j;
+            if (k < K) atomicAdd(&Wg[(long long)n * K + k], acc[i][j]);
+        }
+    }
+}
+
+static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long long M, int N, int K, bool elu_a, cudaStream_t st) {
+    if (!Wg) return SF_OK;
+    const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
+    long long splits = (148LL * 4 + tiles - 1) / tiles;
+    long long max_splits = (M + 255) / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    long long rps = ((M + splits - 1) / splits + 15) / 16 * 16;
+    splits = (M + rps - 1) / rps;
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + 63) / 64), (unsigned)splits);
+    ProfScope ps("bwd_gemm_wgrad_f32", 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)M * N), st);
+    if (elu_a) k_gemm_tn_reduce<true><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
+    else k_gemm_tn_reduce<false><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
+    SF_CHECK_LAUNCH("bwd_gemm_wgrad");
+    return SF_OK;
+}
+
+// out[n] += sum_m G[m][n]
+__global__ void k_colsum(const float* __restrict__ G, float* __restrict__ out, long long M, int N, long long rows_per_block) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float s = 0.f;
+        for (long long m = r0; m < r1; m++) s += G[m * N + n];
+        atomicAdd(&out[n], s);
+    }
+}
+
+static int launch_colsum(const float* G, float* out, long long M, int N, cudaStream_t st) {
+    if (!out) return SF_OK;
+    long long blocks = 148LL * 8;
+    if (blocks > (M + 63) / 64) blocks = (M + 63) / 64;
+    if (blocks < 1) blocks = 1;
+    long long rpb = (M + blocks - 1) / blocks;
+    blocks = (M + rpb - 1) / rpb;
+    int threads = N >= 256 ? 256 : ((N + 31) / 32 * 32);
+    ProfScope ps("bwd_colsum", (double)M * N, 4.0 * (double)M * N, st);
+    k_colsum<<<(unsigned)blocks, threads, 0, st>>>(G, out, M, N, rpb);
+    SF_CHECK_LAUNCH("bwd_colsum");
+    return SF_OK;
+}
+
+// =============================================================================================
+// LayerNorm backward (adjoint of my_layer_norm, a004:54-72), one warp per row.
+//   y = (x - mean) * rstd * gamma + beta ;  gy_eff = ELUOUT ? gy * ELU'(y) : gy
+//   gx (=|+=) rstd * (gyg - mean(gyg) - xhat * mean(gyg * xhat)),  gyg = gy_eff * gamma
+//   ggamma += sum_rows gy_eff * xhat ; gbeta += sum_rows gy_eff
+// =============================================================================================
+template <bool ELUOUT, bool ACCUM>
+__global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ gy, float* __restrict__ gx, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                         long long M, int C, float eps) {
+    extern __shared__ float sacc[];  // [2][C]
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sacc[c] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (; row < M; row += stride) {
+        const float* xr = x + row * C;
+        const float* gr = gy + row * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += xr[c];
+        s = warp_sum(s);
+        const float mean = s / (float)C;
+        float v = 0.f;
+        for (int c = lane; c < C; c += 32) { float d = xr[c] - mean; v += d * d; }
+        v = warp_sum(v);
+        const float rstd = rsqrtf(v / (float)C + eps);
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float xh = (xr[c] - mean) * rstd;
+            float g = gr[c];
+            if (ELUOUT) g *= elu_grad(xh * gamma[c] + beta[c]);
+            float gg = g * gamma[c];
+            s1 += gg;
+            s2 += gg * xh;
+            atomicAdd(&sacc[c], g * xh);
+            atomicAdd(&sacc[C + c], g);
+        }
+        s1 = warp_sum(s1) / (float)C;
+        s2 = warp_sum(s2) / (float)C;
+        for (int c = lane; c < C; c += 32) {
+            float xh = (xr[c] - mean) * rstd;
+            float g = gr[c];
+            if (ELUOUT) g *= elu_grad(xh * gamma[c] + beta[c]);
+            float val = rstd * (g * gamma[c] - s1 - xh * s2);
+            if (ACCUM) val += gx[row * C + c];
+            gx[row * C + c] = val;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (ggamma) atomicAdd(&ggamma[c], sacc[c]);
+        if (gbeta) atomicAdd(&gbeta[c], sacc[C + c]);
+    }
+}
+
+static int launch_ln_bwd(const float* x, const float* gamma, const float* beta, const float* gy, float* gx, float* ggamma,
+                         float* gbeta, long long M, int C, float eps, bool eluout, bool accum, cudaStream_t st) {
+    const int threads = 256;
+    long long blocks = (M * 32 + threads - 1) / threads;
+    if (blocks > 148LL * 4) blocks = 148LL * 4;
+    if (blocks < 1) blocks = 1;
+    size_t smem = 2 * (size_t)C * sizeof(float);
+    ProfScope ps("bwd_layernorm", 20.0 * (double)M * C, 12.0 * (double)M * C, st);
+    if (eluout) {
+        if (accum) k_ln_bwd<true, true><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd<true, false><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+    } else {
+        if (accum) k_ln_bwd<false, true><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd<false, false><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+    }
+    SF_CHECK_LAUNCH("bwd_layernorm");
+    return SF_OK;
+}
+
+// =============================================================================================
+// attention core backward (adjoint of a001:317-354), one (window, head) at a time per CTA
+// =============================================================================================
+// dV = P^T dO ; dP = dO V^T ; dS = P o (dP - rowsum(dP o P)) ; dtable[idx(i,j)] += dS ;
+// dQ = scale * dS K ; dK = scale * dS^T Q.   Masked entries have P = 0 hence dS = 0.
+__global__ void k_attn_core_bwd(const float* __restrict__ Q, const float* __restrict__ Kt, const float* __restrict__ V,
+                                const float* __restrict__ gO, float* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV,
+                                const float* __restrict__ table, float* __restrict__ gtable, WinGeom g, int inner, int nh, int d,
+                                float scale, long long nitems) {
+    extern __shared__ float smb[];
+    const int T = g.T, TS = T + 1;
+    const int tw = 2 * g.wsw - 1, tabn = (2 * g.wsh - 1) * tw;
+    float* Qs = smb;                    // [T][d]
+    float* Ks = Qs + T * d;
+    float* Vs = Ks + T * d;
+    float* Gs = Vs + T * d;             // dO
+    float* Ps = Gs + T * d;             // [T][TS]
+    float* Ss = Ps + T * TS;            // dS [T][TS]
+    float* tab = Ss + T * TS;           // [tabn]
+    float* tacc = tab + tabn;           // [tabn]
+    long long* rows = reinterpret_cast<long long*>(tacc + tabn + ((2 * tabn + 4 * T * d + 2 * T * TS) & 1));
+    int* regs = reinterpret_cast<int*>(rows + T);
+    for (int i = threadIdx.x; i < tabn; i += blockDim.x) { tab[i] = table[i]; tacc[i] = 0.f; }
+
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int win = (int)(item / nh), head = (int)(item % nh);
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            int rg;
+            rows[t] = win_token_src(g, win, t, &rg);
+            regs[t] = rg;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * d; i += blockDim.x) {
+            int t = i / d, dd = i - t * d;
+            long long off = rows[t] * inner + head * d + dd;
+            Qs[i] = Q[off]; Ks[i] = Kt[off]; Vs[i] = V[off]; Gs[i] = gO[off];
+        }
+        __syncthreads();
+        for (int qi = threadIdx.x; qi < T; qi += blockDim.x) {
+            const int qr = qi / g.wsw, qc = qi - qr * g.wsw, qreg = regs[qi];
+            float mx = -INFINITY;
+            for (int j = 0; j < T; j++) {
+                float s = 0.f;
+                for (int dd = 0; dd < d; dd++) s = fmaf(Qs[qi * d + dd], Ks[j * d + dd], s);
+                int jr = j / g.wsw, jc = j - jr * g.wsw;
+                s = s * scale + tab[(jr - qr + g.wsh - 1) * tw + (jc - qc + g.wsw - 1)];
+                if (regs[j] != qreg) s = -1e10f;
+                Ps[qi * TS + j] = s;
+                mx = fmaxf(mx, s);
+            }
+            float sum = 0.f;
+            for (int j = 0; j < T; j++) { float e = expf(Ps[qi * TS + j] - mx); Ps[qi * TS + j] = e; sum += e; }
+            const float inv = 1.f / sum;
+            float delta = 0.f;
+            for (int j = 0; j < T; j++) {
+                float p = Ps[qi * TS + j] * inv;
+                float dp = 0.f;
+                for (int dd = 0; dd < d; dd++) dp = fmaf(Gs[qi * d + dd], Vs[j * d + dd], dp);
+                Ps[qi * TS + j] = p;
+                Ss[qi * TS + j] = dp;
+                delta = fmaf(p, dp, delta);
+            }
+            for (int j = 0; j < T; j++) {
+                float ds = Ps[qi * TS + j] * (Ss[qi * TS + j] - delta);
+                Ss[qi * TS + j] = ds;
+                int jr = j / g.wsw, jc = j - jr * g.wsw;
+                if (gtable && ds != 0.f) atomicAdd(&tacc[(jr - qr + g.wsh - 1) * tw + (jc - qc + g.wsw - 1)], ds);
+            }
+            const long long off = rows[qi] * inner + head * d;
+            for (int dd = 0; dd < d; dd++) {
+                float a = 0.f;
+                for (int j = 0; j < T; j++) a = fmaf(Ss[qi * TS + j], Ks[j * d + dd], a);
+                dQ[off + dd] = a * scale;
+            }
+        }
+        __syncthreads();
+        for (int kj = threadIdx.x; kj < T; kj += blockDim.x) {
+            const long long off = rows[kj] * inner + head * d;
+            for (int dd = 0; dd < d; dd++) {
+                float a = 0.f, b = 0.f;
+                for (int i = 0; i < T; i++) {
+                    a = fmaf(Ss[i * TS + kj], Qs[i * d + dd], a);
+                    b = fmaf(Ps[i * TS + kj], Gs[i * d + dd], b);
+                }
+                dK[off + dd] = a * scale;
+                dV[off + dd] = b;
+            }
+        }
+    }
+    __syncthreads();
+    if (gtable)
+        for (int i = threadIdx.x; i < tabn; i += blockDim.x) atomicAdd(&gtable[i], tacc[i]);
+}
+
+static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
+                                const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st) {
+    const int tabn = (2 * g.wsh - 1) * (2 * g.wsw - 1);
+    size_t smem = ((size_t)4 * g.T * d + 2 * (size_t)g.T * (g.T + 1) + 2 * tabn + 2) * sizeof(float) + (size_t)g.T * 12 + 16;
+    SF_CHECK_ARG(smem <= 200 * 1024, "attention backward: window of %d tokens x head_dim %d needs %zu B of shared memory", g.T, d, smem);
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_attn_core_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { set_error("attention backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
+        configured = true;
+    }
+    const long long nitems = (long long)g.B * g.nWh * g.nWw * nh;
+    int threads = g.T <= 64 ? 64 : (g.T <= 128 ? 128 : 256);
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = 148LL * per_sm;
+    if (grid > nitems) grid = nitems;
+    const double mtok = (double)g.B * g.Hp * g.Wp;
+    ProfScope ps("bwd_attn_core_f32", 12.0 * g.T * mtok * inner, 28.0 * mtok * inner, st);
+    k_attn_core_bwd<<<(unsigned)grid, threads, smem, st>>>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, d, 1.0f / sqrtf((float)d), nitems);
+    SF_CHECK_LAUNCH("bwd_attn_core");
+    return SF_OK;
+}
+
+// =============================================================================================
+// operator backward: window attention
+// =============================================================================================
+static inline void wa_bwd_ln_plan(const sf_window_attn_params* p, bool* need_q, bool* need_kv, bool* share) {
+    const bool self_attn = (p->kv_src == p->q_src);
+    const bool same_ln = self_attn && p->ln_q_gamma == p->ln_kv_gamma && p->ln_q_beta == p->ln_kv_beta;
+    *need_q = p->ln_q_gamma != nullptr;
+    *share = same_ln;                           // kv operand is the very tensor the q operand is
+    *need_kv = p->ln_kv_gamma != nullptr && !same_ln;
+}
+
+size_t window_attn_bwd_ws(const sf_window_attn_bwd_params* bp) {
+    const sf_window_attn_params* p = &bp->fwd;
+    const size_t M = (size_t)p->B * p->Hp * p->Wp, inner = (size_t)p->num_heads * p->head_dim;
+    return 8 * align_up(M * inner * sizeof(float)) + 4 * align_up(M * p->C * sizeof(float));
+}
+
+int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const sf_window_attn_params* p = &bp->fwd;
+    const long long M = (long long)p->B * p->Hp * p->Wp;
+    const int C = p->C, inner = p->num_heads * p->head_dim;
+    Workspace ws(ws_ptr, ws_bytes);
+    float* Q = ws.take<float>((size_t)M * inner);
+    float* K = ws.take<float>((size_t)M * inner);
+    float* V = ws.take<float>((size_t)M * inner);
+    float* O = ws.take<float>((size_t)M * inner);
+    float* gO = ws.take<float>((size_t)M * inner);
+    float* dQ = ws.take<float>((size_t)M * inner);
+    float* dK = ws.take<float>((size_t)M * inner);
+    float* dV = ws.take<float>((size_t)M * inner);
+    float* nqb = ws.take<float>((size_t)M * C);
+    float* nkvb = ws.take<float>((size_t)M * C);
+    float* gnq = ws.take<float>((size_t)M * C);
+    float* gnkv = ws.take<float>((size_t)M * C);
+    if (!Q || !gnkv) { set_error("sf_window_attn_bwd: workspace too small (%zu B given)", ws_bytes); return SF_ERR_WORKSPACE; }
+    bool need_q, need_kv, share;
+    wa_bwd_ln_plan(p, &need_q, &need_kv, &share);
+    const bool self_src = p->kv_src == p->q_src;
+    SF_CHECK_ARG(share || bp->g_kv_src || self_src, "sf_window_attn_bwd: g_kv_src is required for cross attention");
+    // ---- recompute the forward ------------------------------------------------------------------------
+    const float* nq = p->q_src;
+    const float* nkv = p->kv_src;
+    if (need_q) { SF_TRY(launch_layernorm(p->q_src, p->ln_q_gamma, p->ln_q_beta, nqb, M, C, p->ln_eps, 0, nullptr, st)); nq = nqb; }
+    if (share) nkv = nq;
+    else if (need_kv) { SF_TRY(launch_layernorm(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, nkvb, M, C, p->ln_eps, 0, nullptr, st)); nkv = nkvb; }
+    GemmBatch gb{};
+    gb.p[0] = GemmProblem{nq, p->wq, p->bq, nullptr, Q};
+    gb.p[1] = GemmProblem{nkv, p->wk, p->bk, nullptr, K};
+    gb.p[2] = GemmProblem{nkv, p->wv, p->bv, nullptr, V};
+    SF_TRY(launch_gemm_tn(gb, 3, M, inner, C, false, st));
+    WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
+    SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
+    // ---- output projection ----------------------------------------------------------------------------
+    SF_TRY(launch_colsum(bp->gout, bp->g_bo, M, C, st));
+    SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st));
+    SF_TRY(launch_gemm_nn(bp->gout, p->wo, nullptr, gO, M, inner, C, false, st));
+    // ---- attention core ---------------------------------------------------------------------------------
+    SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st));
+    // ---- projections --------------------------------------------------------------------------------------
+    SF_TRY(launch_colsum(dQ, bp->g_bq, M, inner, st));
+    SF_TRY(launch_colsum(dK, bp->g_bk, M, inner, st));
+    SF_TRY(launch_colsum(dV, bp->g_bv, M, inner, st));
+    SF_TRY(launch_gemm_tn_reduce(dQ, nq, bp->g_wq, M, inner, C, false, st));
+    SF_TRY(launch_gemm_tn_reduce(dK, nkv, bp->g_wk, M, inner, C, false, st));
+    SF_TRY(launch_gemm_tn_reduce(dV, nkv, bp->g_wv, M, inner, C, false, st));
+    // gradients w.r.t. the (normalised) operands
+    float* gq_dst = need_q ? gnq : bp->g_q_src;
+    SF_TRY(launch_gemm_nn(dQ, p->wq, nullptr, gq_dst, M, C, inner, false, st));
+    if (share) {
+        SF_TRY(launch_gemm_nn(dK, p->wk, nullptr, gq_dst, M, C, inner, true, st));
+        SF_TRY(launch_gemm_nn(dV, p->wv, nullptr, gq_dst, M, C, inner, true, st));
+    } else {
+        // distinct kv operand (other tensor and/or other LayerNorm)
+        float* gkv_dst = need_kv ? gnkv : (bp->g_kv_src ? bp->g_kv_src : gnkv);
+        SF_TRY(launch_gemm_nn(dK, p->wk, nullptr, gkv_dst, M, C, inner, false, st));
+        SF_TRY(launch_gemm_nn(dV, p->wv, nullptr, gkv_dst, M, C, inner, true, st));
+    }
+    // ---- LayerNorm adjoints -----------------------------------------------------------------------------
+    if (need_q) SF_TRY(launch_ln_bwd(p->q_src, p->ln_q_gamma, p->ln_q_beta, gnq, bp->g_q_src, bp->g_ln_q_gamma, bp->g_ln_q_beta, M, C, p->ln_eps, false, false, st));
+    if (!share) {
+        // where does the kv-side gradient land?  g_kv_src if given, else (same source tensor) it is added to g_q_src
+        float* dst = bp->g_kv_src ? bp->g_kv_src : bp->g_q_src;
+        const bool accum = bp->g_kv_src == nullptr;
+        if (need_kv) {
+            SF_TRY(launch_ln_bwd(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, gnkv, dst, bp->g_ln_kv_gamma, bp->g_ln_kv_beta, M, C, p->ln_eps, false, accum, st));
+        } else if (accum) {
+            SF_TRY(sf_add(bp->g_q_src, gnkv, bp->g_q_src, M * C, (void*)st));
+        }
+    }
+    return SF_OK;
+}
+
+// =============================================================================================
+// operator backward: MLP
+// =============================================================================================
+size_t mlp_bwd_ws(const sf_mlp_bwd_params* bp) {
+    const sf_mlp_params* p = &bp->fwd;
+    return 2 * align_up((size_t)p->M * p->hidden * sizeof(float)) + 2 * align_up((size_t)p->M * p->C * sizeof(float));
+}
+
+int mlp_bwd(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const sf_mlp_params* p = &bp->fwd;
+    const long long M = p->M;
+    const int C = p->C, H = p->hidden;
+    Workspace ws(ws_ptr, ws_bytes);
+    float* hpre = ws.take<float>((size_t)M * H);
+    float* gh = ws.take<float>((size_t)M * H);
+    float* nb = ws.take<float>((size_t)M * C);
+    float* gn = ws.take<float>((size_t)M * C);
+    if (!hpre || !gn) { set_error("sf_mlp_bwd: workspace too small (%zu B given)", ws_bytes); return SF_ERR_WORKSPACE; }
+    const float* n = p->in;
+    if (p->ln_gamma) { SF_TRY(launch_layernorm(p->in, p->ln_gamma, p->ln_beta, nb, M, C, p->ln_eps, 0, nullptr, st)); n = nb; }
+    GemmBatch g1{};
+    g1.p[0] = GemmProblem{n, p->w1, p->b1, nullptr, hpre};
+    SF_TRY(launch_gemm_tn(g1, 1, M, H, C, false, st));
+    SF_TRY(launch_colsum(bp->gout, bp->g_b2, M, C, st));
+    SF_TRY(launch_gemm_tn_reduce(bp->gout, hpre, bp->g_w2, M, C, H, true, st));      // gW2 = gout^T ELU(hpre)
+    SF_TRY(launch_gemm_nn(bp->gout, p->w2, hpre, gh, M, H, C, false, st));           // g_hpre = (gout W2) o ELU'(hpre)
+    SF_TRY(launch_colsum(gh, bp->g_b1, M, H, st));
+    SF_TRY(launch_gemm_tn_reduce(gh, n, bp->g_w1, M, H, C, false, st));
+    float* gdst = p->ln_gamma ? gn : bp->g_in;
+    SF_TRY(launch_gemm_nn(gh, p->w1, nullptr, gdst, M, C, H, false, st));
+    if (p->ln_gamma) SF_TRY(launch_ln_bwd(p->in, p->ln_gamma, p->ln_beta, gn, bp->g_in, bp->g_ln_gamma, bp->g_ln_beta, M, C, p->ln_eps, false, false, st));
+    return SF_OK;
+}
+
+// =============================================================================================
+// operator backward: patch layers
+// =============================================================================================
+size_t patch_bwd_ws(const sf_patch_bwd_params* bp) {
+    const sf_patch_params* p = &bp->fwd;
+    const int mm = p->mh * p->mw;
+    const size_t Mr = p->encoder ? (size_t)p->B * (p->H / p->mh) * (p->W / p->mw) : (size_t)p->B * p->H * p->W;
+    const size_t K = p->encoder ? (size_t)mm * p->Cin : (size_t)p->Cin, N = p->encoder ? (size_t)p->Cout : (size_t)mm * p->Cout;
+    return 2 * align_up(Mr * K * sizeof(float)) + 3 * align_up(Mr * N * sizeof(float));
+}
+
+int patch_bwd(const sf_patch_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const sf_patch_params* p = &bp->fwd;
+    const int mm = p->mh * p->mw;
+    const long long Mr = p->encoder ? (long long)p->B * (p->H / p->mh) * (p->W / p->mw) : (long long)p->B * p->H * p->W;
+    const int K = p->encoder ? mm * p->Cin : p->Cin, N = p->encoder ? p->Cout : mm * p->Cout;
+    Workspace ws(ws_ptr, ws_bytes);
+    float* Abuf = ws.take<float>((size_t)Mr * K);
+    float* gA = ws.take<float>((size_t)Mr * K);
+    float* lin = ws.take<float>((size_t)Mr * N);
+    float* glin = ws.take<float>((size_t)Mr * N);
+    float* gpost = ws.take<float>((size_t)Mr * N);
+    if (!Abuf || !gpost) { set_error("sf_patch_bwd: workspace too small (%zu B given)", ws_bytes); return SF_ERR_WORKSPACE; }
+    const float* A = p->in;
+    if (p->encoder) { SF_TRY(sf_patch_merge(p->in, Abuf, p->B, p->H, p->W, p->Cin, p->mh, p->mw, (void*)st)); A = Abuf; }
+    GemmBatch g{};
+    g.p[0] = GemmProblem{A, p->w, p->b, nullptr, lin};
+    SF_TRY(launch_gemm_tn(g, 1, Mr, N, K, false, st));
+    // gradient w.r.t. the LayerNorm output rows (ELU' is applied inside the LN backward kernel)
+    const float* gy = bp->gout;
+    if (!p->encoder) { SF_TRY(sf_patch_merge(bp->gout, gpost, p->B, p->H * p->mh, p->W * p->mw, p->Cout, p->mh, p->mw, (void*)st)); gy = gpost; }
+    SF_TRY(launch_ln_bwd(lin, p->ln_gamma, p->ln_beta, gy, glin, bp->g_ln_gamma, bp->g_ln_beta, Mr, N, p->ln_eps, true, false, st));
+    SF_TRY(launch_colsum(glin, bp->g_b, Mr, N, st));
+    SF_TRY(launch_gemm_tn_reduce(glin, A, bp->g_w, Mr, N, K, false, st));
+    if (p->encoder) {
+        SF_TRY(launch_gemm_nn(glin, p->w, nullptr, gA, Mr, K, N, false, st));
+        SF_TRY(sf_patch_unmerge(gA, bp->g_in, p->B, p->H / p->mh, p->W / p->mw, p->Cin, p->mh, p->mw, (void*)st));
+    } else {
+        SF_TRY(launch_gemm_nn(glin, p->w, nullptr, bp->g_in, Mr, K, N, false, st));
+    }
+    return SF_OK;
+}
+
+// =============================================================================================
+// operator backward: final head (a013:126-152)
+// =============================================================================================
+static constexpr int HB_THREADS = 256;
+static constexpr int HB_MAXK = 7;
+
+// forward conv1 recompute: t[pix] = conv(x,y) (same arithmetic as k_head_conv1)
+__global__ void k_hb_conv1(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w1, const float* __restrict__ b1,
+                           float2* __restrict__ t, int B, int H, int W, int ks) {
+    const int pad = ks / 2;
+    long long total = (long long)B * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % W);
+        long long p = i / W;
+        int r = (int)(p % H);
+        long long b = p / H;
+        const float* xb = x + b * H * W;
+        const float* yb = y + b * H * W;
+        float o0 = b1[0], o1 = b1[1];
+        for (int dr = 0; dr < ks; dr++) {
+            int rr = reflect_both(r + dr - pad, H);
+            for (int dc = 0; dc < ks; dc++) {
+                int cc = reflect_both(c + dc - pad, W);
+                float xv = xb[(long long)rr * W + cc], yv = yb[(long long)rr * W + cc];
+                int wi = dr * ks + dc;
+                o0 = fmaf(w1[(0 * 2 + 0) * ks * ks + wi], xv, o0); o0 = fmaf(w1[(0 * 2 + 1) * ks * ks + wi], yv, o0);
+                o1 = fmaf(w1[(1 * 2 + 0) * ks * ks + wi], xv, o1); o1 = fmaf(w1[(1 * 2 + 1) * ks * ks + wi], yv, o1);
+            }
+        }
+        t[i] = make_float2(o0, o1);
+    }
+}
+
+__device__ __forceinline__ void block_atomic_add(float v, float* dst, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) a += red[k];
+        atomicAdd(dst, a);
+    }
+}
+
+// conv2 adjoint: ga[p'] += gout[p] * w2[c][tap] (scatter, reflect), gw2[c][tap] += gout[p] * a[p'], gb2 += gout
+__global__ void k_hb_conv2_bwd(const float* __restrict__ gout, const float2* __restrict__ t, const float* __restrict__ affine,
+                               const float* __restrict__ w2, float* __restrict__ ga, float* __restrict__ gw2, float* __restrict__ gb2,
+                               int B, int H, int W, int ks) {
+    __shared__ float red[HB_THREADS / 32];
+    const float sc0 = affine[0], sh0 = affine[1], sc1 = affine[2], sh1 = affine[3];
+    const int pad = ks / 2;
+    long long total = (long long)B * H * W;
+    float gb = 0.f;
+    float gw[2 * HB_MAXK * HB_MAXK];
+    for (int i = 0; i < 2 * ks * ks; i++) gw[i] = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % W);
+        long long p = i / W;
+        int r = (int)(p % H);
+        long long b = p / H;
+        const float go = gout[i];
+        gb += go;
+        for (int dr = 0; dr < ks; dr++) {
+            int rr = reflect_both(r + dr - pad, H);
+            for (int dc = 0; dc < ks; dc++) {
+                int cc = reflect_both(c + dc - pad, W);
+                long long q = (b * H + rr) * W + cc;
+                float2 tv = t[q];
+                float a0 = elu1(fmaf(tv.x, sc0, sh0)), a1 = elu1(fmaf(tv.y, sc1, sh1));
+                gw[dr * ks + dc] += go * a0;
+                gw[ks * ks + dr * ks + dc] += go * a1;
+                atomicAdd(&ga[2 * q], go * w2[dr * ks + dc]);
+                atomicAdd(&ga[2 * q + 1], go * w2[ks * ks + dr * ks + dc]);
+            }
+        }
+    }
+    block_atomic_add(gb, gb2, red);
+    for (int i = 0; i < 2 * ks * ks; i++) block_atomic_add(gw[i], &gw2[i], red);
+}
+
+// gz = ga * ELU'(z); per-channel sums: stats[0..1] = sum gz, stats[2..3] = sum gz * zhat
+__global__ void k_hb_bn_stats(const float* __restrict__ ga, const float2* __restrict__ t, const float* __restrict__ affine,
+                              const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ gz,
+                              float* __restrict__ stats, long long total) {
+    __shared__ float red[HB_THREADS / 32];
+    const float sc0 = affine[0], sh0 = affine[1], sc1 = affine[2], sh1 = affine[3];
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float2 tv = t[i];
+        float g0 = ga[2 * i] * elu_grad(fmaf(tv.x, sc0, sh0)), g1 = ga[2 * i + 1] * elu_grad(fmaf(tv.y, sc1, sh1));
+        gz[2 * i] = g0; gz[2 * i + 1] = g1;
+        s0 += g0; s1 += g1;
+        q0 += g0 * (tv.x - mean[0]) * invstd[0];
+        q1 += g1 * (tv.y - mean[1]) * invstd[1];
+    }
+    block_atomic_add(s0, &stats[0], red);
+    block_atomic_add(s1, &stats[1], red);
+    block_atomic_add(q0, &stats[2], red);
+    block_atomic_add(q1, &stats[3], red);
+}
+
+// gt = BN adjoint of gz (training: batch statistics; eval: gz * scale); then conv1 adjoint (scatter)
+__global__ void k_hb_conv1_bwd(const float* __restrict__ gz, const float2* __restrict__ t, const float* __restrict__ stats,
+                               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                               const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w1,
+                               float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gw1, float* __restrict__ gb1,
+                               int B, int H, int W, int ks, int training) {
+    __shared__ float red[HB_THREADS / 32];
+    const int pad = ks / 2;
+    long long total = (long long)B * H * W;
+    const float invn = 1.f / (float)total;
+    float gb[2] = {0.f, 0.f};
+    float gw[4 * HB_MAXK * HB_MAXK];
+    for (int i = 0; i < 4 * ks * ks; i++) gw[i] = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % W);
+        long long p = i / W;
+        int r = (int)(p % H);
+        long long b = p / H;
+        float2 tv = t[i];
+        float gt[2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+            float g = gz[2 * i + ch];
+            float tvc = ch == 0 ? tv.x : tv.y;
+            if (training) {
+                float zh = (tvc - mean[ch]) * invstd[ch];
+                gt[ch] = gamma[ch] * invstd[ch] * (g - stats[ch] * invn - zh * stats[2 + ch] * invn);
+            } else {
+                gt[ch] = g * gamma[ch] * invstd[ch];
+            }
+            gb[ch] += gt[ch];
+        }
+        const float* xb = x + b * H * W;
+        const float* yb = y + b * H * W;
+        for (int dr = 0; dr < ks; dr++) {
+            int rr = reflect_both(r + dr - pad, H);
+            for (int dc = 0; dc < ks; dc++) {
+                int cc = reflect_both(c + dc - pad, W);
+                long long q = (b * H + rr) * W + cc;
+                int wi = dr * ks + dc;
+                float xv = xb[(long long)rr * W + cc], yv = yb[(long long)rr * W + cc];
+                gw[(0 * 2 + 0) * ks * ks + wi] += gt[0] * xv; gw[(0 * 2 + 1) * ks * ks + wi] += gt[0] * yv;
+                gw[(1 * 2 + 0) * ks * ks + wi] += gt[1] * xv; gw[(1 * 2 + 1) * ks * ks + wi] += gt[1] * yv;
+                atomicAdd(&gx[q], gt[0] * w1[(0 * 2 + 0) * ks * ks + wi] + gt[1] * w1[(1 * 2 + 0) * ks * ks + wi]);
+                atomicAdd(&gy[q], gt[0] * w1[(0 * 2 + 1) * ks * ks + wi] + gt[1] * w1[(1 * 2 + 1) * ks * ks + wi]);
+            }
+        }
+    }
+    block_atomic_add(gb[0], &gb1[0], red);
+    block_atomic_add(gb[1], &gb1[1], red);
+    for (int i = 0; i < 4 * ks * ks; i++) block_atomic_add(gw[i], &gw1[i], red);
+}
+
+// tiny helper: affine / mean / invstd vectors for the backward, and the BN affine gradients
+__global__ void k_hb_prepare(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ running_mean,
+                             const float* __restrict__ running_var, const float* __restrict__ save_mean,
+                             const float* __restrict__ save_invstd, float* __restrict__ vec, float eps, int training) {
+    // vec: [0..3] affine (sc0, sh0, sc1, sh1), [4..5] mean, [6..7] invstd, [8..11] stats (zeroed)
+    int c = threadIdx.x;
+    if (c < 2) {
+        float mean = training ? save_mean[c] : running_mean[c];
+        float invstd = training ? save_invstd[c] : 1.0f / sqrtf(running_var[c] + eps);
+        float sc = gamma[c] * invstd;
+        vec[2 * c] = sc;
+        vec[2 * c + 1] = beta[c] - mean * sc;
+        vec[4 + c] = mean;
+        vec[6 + c] = invstd;
+    }
+    if (c < 4) vec[8 + c] = 0.f;
+}
+
+__global__ void k_hb_bn_param_grads(const float* __restrict__ stats, float* __restrict__ ggamma, float* __restrict__ gbeta) {
+    int c = threadIdx.x;
+    if (c < 2) {
+        if (gbeta) atomicAdd(&gbeta[c], stats[c]);
+        if (ggamma) atomicAdd(&ggamma[c], stats[2 + c]);
+    }
+}
+
+__global__ void k_zero(float* __restrict__ p, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+size_t head_bwd_ws(const sf_head_bwd_params* bp) {
+    const sf_head_params* p = &bp->fwd;
+    const size_t total = (size_t)p->B * p->H * p->W;
+    return 3 * align_up(total * 2 * sizeof(float)) + align_up(16 * sizeof(float));
+}
+
+int head_bwd(const sf_head_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const sf_head_params* p = &bp->fwd;
+    const long long total = (long long)p->B * p->H * p->W;
+    SF_CHECK_ARG(bp->g_w1 && bp->g_b1 && bp->g_w2 && bp->g_b2, "sf_head_bwd: weight gradient buffers are required");
+    SF_CHECK_ARG(!p->training || (p->save_mean && p->save_invstd), "sf_head_bwd: training needs the saved batch statistics");
+    Workspace ws(ws_ptr, ws_bytes);
+    float2* t = ws.take<float2>((size_t)total);
+    float* ga = ws.take<float>((size_t)total * 2);
+    float* gz = ws.take<float>((size_t)total * 2);
+    float* vec = ws.take<float>(16);
+    if (!t || !vec) { set_error("sf_head_bwd: workspace too small (%zu B given)", ws_bytes); return SF_ERR_WORKSPACE; }
+    long long nb = (total + HB_THREADS - 1) / HB_THREADS;
+    if (nb > 148LL * 8) nb = 148LL * 8;
+    const int blocks = (int)nb;
+    ProfScope ps("bwd_final_head", 200.0 * (double)total, 60.0 * (double)total, st);
+    k_hb_prepare<<<1, 32, 0, st>>>(p->bn_gamma, p->bn_beta, p->running_mean, p->running_var, p->save_mean, p->save_invstd, vec, p->bn_eps, p->training);
+    SF_CHECK_LAUNCH("hb_prepare");
+    k_hb_conv1<<<blocks, HB_THREADS, 0, st>>>(p->x, p->y, p->w1, p->b1, t, p->B, p->H, p->W, p->ksize);
+    SF_CHECK_LAUNCH("hb_conv1");
+    k_zero<<<blocks, HB_THREADS, 0, st>>>(ga, total * 2);
+    SF_CHECK_LAUNCH("hb_zero");
+    k_zero<<<blocks, HB_THREADS, 0, st>>>(bp->g_x, total);
+    SF_CHECK_LAUNCH("hb_zero");
+    k_zero<<<blocks, HB_THREADS, 0, st>>>(bp->g_y, total);
+    SF_CHECK_LAUNCH("hb_zero");
+    k_hb_conv2_bwd<<<blocks, HB_THREADS, 0, st>>>(bp->gout, t, vec, p->w2, ga, bp->g_w2, bp->g_b2, p->B, p->H, p->W, p->ksize);
+    SF_CHECK_LAUNCH("hb_conv2_bwd");
+    k_hb_bn_stats<<<blocks, HB_THREADS, 0, st>>>(ga, t, vec, vec + 4, vec + 6, gz, vec + 8, total);
+    SF_CHECK_LAUNCH("hb_bn_stats");
+    k_hb_bn_param_grads<<<1, 32, 0, st>>>(vec + 8, bp->g_bn_gamma, bp->g_bn_beta);
+    SF_CHECK_LAUNCH("hb_bn_param_grads");
+    k_hb_conv1_bwd<<<blocks, HB_THREADS, 0, st>>>(gz, t, vec + 8, p->bn_gamma, vec + 4, vec + 6, p->x, p->y, p->w1, bp->g_x, bp->g_y,
+                                                  bp->g_w1, bp->g_b1, p->B, p->H, p->W, p->ksize, p->training);
+    SF_CHECK_LAUNCH("hb_conv1_bwd");
+    return SF_OK;
+}
+
 }  // namespace sf

@@ -1,0 +1,184 @@
+"""Gradient parity: the CUDA backward kernels against the reference's own
+autograd gradients stored in the golden fixtures, and against autograd over the oracle."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import fusion_oracle as fo
+from oracle.make_golden import small_cfg
+from tests.util import build_model, dropin, golden, rel_err, wa_cases
+
+pytestmark = pytest.mark.gpu
+TOL_GRAD = 2e-4   # fp32 backward, relative to the largest entry of each gradient tensor
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_window_attention_gradients_golden():
+    dropin()
+    from a001_WindowAttention import WindowAttention
+    g, cases = wa_cases()
+    for c in cases:
+        t = c["tag"]
+        wa = WindowAttention(in_out_dims=c["c"], num_heads=c["nh"], dims_per_head=c["d"], window_size=(7, 7),
+                             use_cyclic_shift=c["shifted"], use_cross_attention=c["cross"], use_qkv_bias=True,
+                             attention_drop_ratio=0.0, linear_after_att_drop_ratio=0.0)
+        wa.load_state_dict({k[len(t) + 3:]: T(g[k]) for k in g.files if k.startswith(t + "/p/")})
+        wa = wa.cuda()
+        q = T(g[t + "/q"]).cuda().requires_grad_(True)
+        kv = T(g[t + "/kv"]).cuda().requires_grad_(True) if c["cross"] else q
+        out = wa(q, kv, kv)
+        (out * T(g[t + "/gout"]).cuda()).sum().backward()
+        assert rel_err(q.grad, T(g[t + "/gq"])) <= TOL_GRAD, (t, "gq", rel_err(q.grad, T(g[t + "/gq"])))
+        if c["cross"]:
+            assert rel_err(kv.grad, T(g[t + "/gkv"])) <= TOL_GRAD, (t, "gkv")
+        # k_for_heads.bias has an analytically ZERO gradient (softmax is invariant to a per-row shift of
+        # the scores); both sides hold round-off there, so errors are measured against the largest
+        # parameter gradient of the module, with each tensor's own maximum when that is larger.
+        gscale = max(float(np.abs(g[f"{t}/g/{n}"]).max()) for n, _ in wa.named_parameters())
+        for n, prm in wa.named_parameters():
+            ref = T(g[f"{t}/g/{n}"])
+            assert prm.grad is not None, (t, n)
+            err = float((prm.grad.cpu() - ref).abs().max()) / max(float(ref.abs().max()), 0.05 * gscale)
+            assert err <= TOL_GRAD, (t, n, err)
+
+
+def _oracle_grads(fn, tensors):
+    leaves = [t.clone().requires_grad_(True) for t in tensors]
+    out = fn(*leaves)
+    return out, leaves
+
+
+def test_mlp_and_prenorm_gradients_vs_oracle_autograd():
+    sw = dropin()
+    g = torch.Generator().manual_seed(5)
+    c, hid = 16, 40
+    x = torch.randn(2, c, 9, 7, generator=g)
+    w1, b1 = torch.randn(hid, c, 1, 1, generator=g) * 0.3, 0.1 * torch.randn(hid, generator=g)
+    w2, b2 = torch.randn(c, hid, 1, 1, generator=g) * 0.3, 0.1 * torch.randn(c, generator=g)
+    lg, lb = 1 + 0.2 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    go = torch.randn(2, c, 9, 7, generator=g)
+    ref_in = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2, lg, lb)]
+    rx, rw1, rb1, rw2, rb2, rlg, rlb = ref_in
+    ref = rx + torch.nn.functional.conv2d(torch.nn.functional.elu(torch.nn.functional.conv2d(fo.layer_norm_c(rx, rlg, rlb), rw1, rb1)), rw2, rb2)
+    (ref * go).sum().backward()
+    cu = [t.clone().cuda().requires_grad_(True) for t in (x, w1, b1, w2, b2, lg, lb)]
+    cx, cw1, cb1, cw2, cb2, clg, clb = cu
+    out = sw.ops.mlp(cx, w1=cw1, b1=cb1, w2=cw2, b2=cb2, ln=(clg, clb), residual=cx, precision="fp32")
+    (out * go.cuda()).sum().backward()
+    for a, b, n in zip(cu, ref_in, "x w1 b1 w2 b2 ln_g ln_b".split()):
+        assert rel_err(a.grad, b.grad) <= TOL_GRAD, (n, rel_err(a.grad, b.grad))
+
+
+@pytest.mark.parametrize("encoder", [True, False])
+def test_patch_layer_gradients_vs_oracle_autograd(encoder):
+    sw = dropin()
+    g = torch.Generator().manual_seed(8)
+    cin, cout = (6, 16) if encoder else (16, 6)
+    kin, kout = (cin * 4, cout) if encoder else (cin, cout * 4)
+    x = torch.randn(2, cin, 10, 12, generator=g)
+    p = {"mlp_layer_x.weight": torch.randn(kout, kin, 1, 1, generator=g) * 0.3, "mlp_layer_x.bias": 0.1 * torch.randn(kout, generator=g),
+         "layer_norm_x.weight": 1 + 0.2 * torch.randn(kout, generator=g), "layer_norm_x.bias": 0.1 * torch.randn(kout, generator=g)}
+    keys = list(p)
+    ref_leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    rx = x.clone().requires_grad_(True)
+    ref = fo.patch_layer(rx, ref_leaves, "", "x", encoder, (2, 2))
+    go = torch.randn(ref.shape, generator=g)
+    (ref * go).sum().backward()
+    cu = {k: v.clone().cuda().requires_grad_(True) for k, v in p.items()}
+    cx = x.clone().cuda().requires_grad_(True)
+    out = sw.ops.patch_layer(cx, w=cu[keys[0]], b=cu[keys[1]], ln_gamma=cu[keys[2]], ln_beta=cu[keys[3]], encoder=encoder,
+                             merging_size=(2, 2), out_dims=cout, precision="fp32")
+    assert rel_err(out, ref) <= 1e-4
+    (out * go.cuda()).sum().backward()
+    assert rel_err(cx.grad, rx.grad) <= TOL_GRAD
+    for k in keys:
+        assert rel_err(cu[k].grad, ref_leaves[k].grad) <= TOL_GRAD, (k, rel_err(cu[k].grad, ref_leaves[k].grad))
+
+
+def test_pad_crop_gradients():
+    sw = dropin()
+    x = torch.randn(2, 4, 9, 11, requires_grad=True)
+    ref = torch.nn.functional.pad(x, (0, 3, 0, 5), mode="reflect")
+    go = torch.randn(ref.shape)
+    (ref * go).sum().backward()
+    cx = x.detach().clone().cuda().requires_grad_(True)
+    out = sw.ops.pad_reflect(cx, 5, 3)
+    (out * go.cuda()).sum().backward()
+    assert torch.allclose(cx.grad.cpu(), x.grad, atol=1e-6)
+    y = torch.randn(2, 4, 9, 11, requires_grad=True)
+    s = torch.randn(2, 4, 7, 10, requires_grad=True)
+    ref = y[:, :, :7, :10] + s
+    go = torch.randn(ref.shape)
+    (ref * go).sum().backward()
+    cy, cs = y.detach().clone().cuda().requires_grad_(True), s.detach().clone().cuda().requires_grad_(True)
+    out = sw.ops.crop(cy, 2, 1, add=cs)
+    (out * go.cuda()).sum().backward()
+    assert torch.equal(cy.grad.cpu(), y.grad) and torch.equal(cs.grad.cpu(), s.grad)
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_final_head_gradients_vs_oracle_autograd(training):
+    sw = dropin()
+    g = torch.Generator().manual_seed(3)
+    x, y = torch.randn(2, 1, 13, 17, generator=g), torch.randn(2, 1, 13, 17, generator=g)
+    p = {"final_layer.0.weight": torch.randn(2, 2, 3, 3, generator=g) * 0.4, "final_layer.0.bias": 0.1 * torch.randn(2, generator=g),
+         "final_layer.1.weight": 1 + 0.2 * torch.randn(2, generator=g), "final_layer.1.bias": 0.1 * torch.randn(2, generator=g),
+         "final_layer.1.running_mean": 0.1 * torch.randn(2, generator=g), "final_layer.1.running_var": 0.5 + torch.rand(2, generator=g),
+         "final_layer.3.weight": torch.randn(1, 2, 3, 3, generator=g) * 0.4, "final_layer.3.bias": 0.1 * torch.randn(1, generator=g)}
+    learn = [k for k in p if "running" not in k]
+    ref_p = {k: (v.clone().requires_grad_(True) if k in learn else v.clone()) for k, v in p.items()}
+    rx, ry = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    ref = fo.final_head(rx, ry, ref_p, training=training)
+    go = torch.randn(ref.shape, generator=g)
+    (ref * go).sum().backward()
+    cu = {k: (v.clone().cuda().requires_grad_(True) if k in learn else v.clone().cuda()) for k, v in p.items()}
+    cx, cy = x.clone().cuda().requires_grad_(True), y.clone().cuda().requires_grad_(True)
+    out = sw.ops.final_head(cx, cy, w1=cu["final_layer.0.weight"], b1=cu["final_layer.0.bias"], bn_gamma=cu["final_layer.1.weight"],
+                            bn_beta=cu["final_layer.1.bias"], running_mean=cu["final_layer.1.running_mean"],
+                            running_var=cu["final_layer.1.running_var"], w2=cu["final_layer.3.weight"], b2=cu["final_layer.3.bias"],
+                            training=training)
+    assert rel_err(out, ref) <= 1e-4
+    (out * go.cuda()).sum().backward()
+    assert rel_err(cx.grad, rx.grad) <= TOL_GRAD and rel_err(cy.grad, ry.grad) <= TOL_GRAD
+    gmax = max(float(ref_p[k].grad.abs().max()) for k in learn)
+    for k in learn:
+        if training and k == "final_layer.0.bias":
+            # batch-stat BatchNorm removes the conv bias: its gradient is analytically zero
+            assert float(cu[k].grad.abs().max()) <= 1e-4 * gmax
+            continue
+        assert rel_err(cu[k].grad, ref_p[k].grad) <= TOL_GRAD, (k, rel_err(cu[k].grad, ref_p[k].grad))
+
+
+def test_small_model_training_step_gradients_match_reference_autograd():
+    """Whole model, train mode (batch-stat BatchNorm), every one of the parameter gradients."""
+    g = golden("model_small.npz")
+    cfg = small_cfg()
+    m = build_model(cfg, act=nn.ELU()).train()
+    m.load_state_dict(fo.synth_state_dict(cfg, seed=3), strict=True)
+    ir, vis = fo.synth_inputs(2, 37, 45, seed=5)
+    out = m(ir.cuda(), vis.cuda())
+    assert rel_err(out, T(g["out_train"])) <= 1e-4
+    (out * T(g["grad_weight"]).cuda()).sum().backward()
+    seen, n, worst = set(), 0, (0.0, "")
+    gscale = float(np.median([np.abs(g[k]).max() for k in g.files if k.startswith("grad::")]))
+    for name, prm in m.named_parameters():
+        if id(prm) in seen:
+            continue
+        seen.add(id(prm))
+        ref = T(g["grad::" + name])
+        assert prm.grad is not None, name
+        if name.endswith("k_for_heads.bias") or name == "final_layer.0.bias":
+            # analytically zero gradients (softmax shift invariance; batch-stat BatchNorm removes the
+            # conv bias): both sides hold round-off only
+            assert float(prm.grad.abs().max()) <= 1e-3 * gscale, name
+            n += 1
+            continue
+        e = float((prm.grad.cpu() - ref).abs().max()) / max(float(ref.abs().max()), 0.05 * gscale)
+        worst = max(worst, (e, name))
+        n += 1
+    assert n > 100
+    assert worst[0] <= 1e-3, worst
