@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="image pairs per GPU per step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE configs[1] (default, headline); train: configs[2] training step")
+    ap.add_argument("--batch", type=int, default=None, help="image pairs per GPU per step (64 infer / 32 train)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--precision", default=os.environ.get("SWINFUSE_BENCH_PRECISION", "auto"))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
@@ -332,8 +334,81 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, rank: int, world: int, local_rank: int):
+    """BASELINE configs[2]: training step = forward -> clamp -> loss -> backward -> gradient all-reduce -> Adam,
+    batch 32 pairs per GPU, data parallel.  Forward in `precision`, backward kernels fp32."""
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    precision = pick_precision(args.precision)
+    model, swinfuse = build_model(precision)
+    model.train()
+    from swinfuse.loss_ops import FusionLoss
+    from swinfuse.train import DataParallelTrainer
+    loss_fn = FusionLoss().to(dev)
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-2)
+    B, S = args.batch, args.size
+    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    ir = torch.rand(B, 1, S, S, generator=g).to(dev)
+    vis = torch.rand(B, 1, S, S, generator=g).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ops = swinfuse.ops
+    ops.reset_launch_count()
+    loss0 = trainer.step(ir, vis)
+    launches = ops.launch_count()
+    for _ in range(max(0, args.warmup - 1)):
+        trainer.step(ir, vis)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(ir, vis)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    prof = {}
+    if rank == 0:
+        ops.profile_enable(True)
+    trainer.step(ir, vis)   # attribution pass: every rank steps (the step contains the gradient all-reduce)
+    torch.cuda.synchronize()
+    if rank == 0:
+        prof = ops.profile_summary()
+        ops.profile_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank != 0:
+        return
+    pairs = B * world * args.steps
+    kernels = {k: {"launches_per_step": v["launches"], "ms_per_step": v["total_ms"]} for k, v in
+               sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}
+    line = {"metric": "training image pairs/sec", "value": pairs / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "steps_per_s": args.steps / (ms / 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision + " fwd / fp32 bwd",
+            "data": "synthetic",
+            "config": {"workload": f"training step B={B}/GPU {S}x{S} pairs, data parallel (BASELINE configs[2])",
+                       "global_batch": B * world, "loss": "a008 semantics via swinfuse.loss_ops (torch ops, parity unpinned)",
+                       "optimizer": "Adam lr 1e-2, sf_adam_step over one flat buffer",
+                       "collective": "one NCCL all-reduce of the flat fp32 gradient buffer" if world > 1 else "none",
+                       "launch": "eager"},
+            "gpu_launches": launches * args.steps, "loss_first": float(loss0), "loss_last": float(loss), "clocks": clocks,
+            "model_tflops": pairs / (ms / 1e3) * 3 * GFLOP_PER_PAIR_256 * (S / 256.0) ** 2 / 1e3, "kernels": kernels}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
+    if args.batch is None:
+        args.batch = 64 if args.mode == "infer" else 32
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -345,7 +420,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.mode == "train":
+            run_train(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

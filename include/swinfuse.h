@@ -246,6 +246,12 @@ typedef struct {
 size_t sf_head_bwd_workspace_bytes(const sf_head_bwd_params* p);
 int sf_head_bwd(const sf_head_bwd_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One Adam step (torch.optim.Adam semantics, a016:67: no weight decay, no amsgrad) over flat fp32
+ * buffers of n elements: g' = grad * grad_scale (1/world_size after the data-parallel all-reduce);
+ * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
+int sf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* out[i] = a[i] + b[i]  (U-Net skip when no crop precedes it) */
 int sf_add(const float* a, const float* b, float* out, long long n, void* stream);
 

@@ -1,5 +1,7 @@
 // C ABI entry points: argument validation and dispatch on `precision`.
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <map>
 #include <string>
 #include <vector>
@@ -10,7 +12,7 @@
 namespace sf {
 
 static thread_local char g_err[512] = "";
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide: autograd runs backward kernels on its own thread
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -21,7 +23,9 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches += n; }
 
 const char* prof_name(const char* fmt, int v) {
-    static thread_local std::map<std::string, std::string>* pool = nullptr;
+    static std::map<std::string, std::string>* pool = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
     if (!pool) pool = new std::map<std::string, std::string>();
     char buf[64];
     snprintf(buf, sizeof(buf), fmt, v);
@@ -31,22 +35,26 @@ const char* prof_name(const char* fmt, int v) {
 }
 
 struct ProfRecord { const char* name; double flops, bytes; cudaEvent_t e0, e1; };
-static thread_local bool g_prof_on = false;
-static thread_local std::vector<ProfRecord>* g_prof = nullptr;
+static std::atomic<bool> g_prof_on{false};
+static std::vector<ProfRecord>* g_prof = nullptr;
+static std::mutex g_prof_mu;
 
 ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t stream) : rec(-1), st(stream) {
     if (!g_prof_on) return;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
-    if (!g_prof) g_prof = new std::vector<ProfRecord>();
     ProfRecord r{name, flops, bytes, nullptr, nullptr};
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
     cudaEventRecord(r.e0, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof) g_prof = new std::vector<ProfRecord>();
     g_prof->push_back(r);
     rec = (int)g_prof->size() - 1;
 }
 ProfScope::~ProfScope() {
-    if (rec >= 0) cudaEventRecord((*g_prof)[rec].e1, st);
+    if (rec < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof && rec < (int)g_prof->size()) cudaEventRecord((*g_prof)[rec].e1, st);
 }
 
 static int check_wa(const sf_window_attn_params* p, const char* who) {
@@ -104,6 +112,7 @@ int sf_profile_enable(int on) {
 
 int sf_profile_summary(sf_profile_entry* out, int max_entries) {
     SF_CHECK_ARG(out && max_entries > 0, "sf_profile_summary: bad args");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!g_prof) return 0;
     std::map<std::string, sf_profile_entry> agg;
     for (auto& r : *g_prof) {

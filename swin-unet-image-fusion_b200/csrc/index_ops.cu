@@ -2,6 +2,7 @@
 // einops / F.pad / torch.roll (SURVEY.md section 8 rows a2, a3, a13, a14/a15 index parts).
 // All are HBM-bound: one pass, channel-innermost so a warp touches contiguous bytes,
 // 128-bit accesses when C % 4 == 0, grid sized to a multiple of the SM count.
+#include <cmath>
 #include "common.cuh"
 
 namespace sf {
@@ -196,6 +197,18 @@ __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, 
         out[i] = a[i] + b[i];
 }
 
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                       float step_size, float b1, float b2, float inv_sqrt_bc2, float eps, float gscale) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    }
+}
+
 static inline bool vec4_ok(int C, const void* a, const void* b, const void* c = nullptr) {
     auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     return (C % 4 == 0) && al(a) && al(b) && al(c);
@@ -371,6 +384,17 @@ int sf_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, voi
 }
 int sf_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, void* stream) {
     return transpose_launch("sf_nhwc_to_nchw", in, out, B, H * W, C, stream);
+}
+
+int sf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                 float eps, int step, float grad_scale, void* stream) {
+    SF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "sf_adam_step: bad args");
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    ProfScope ps("adam_step", 12.0 * (double)n, 28.0 * (double)n, as_stream(stream));
+    k_adam<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), beta1, beta2,
+                                                             (float)(1.0 / sqrt(bc2)), eps, grad_scale);
+    SF_CHECK_LAUNCH("sf_adam_step");
+    return SF_OK;
 }
 
 int sf_add(const float* a, const float* b, float* out, long long n, void* stream) {

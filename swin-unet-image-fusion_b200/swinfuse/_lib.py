@@ -113,6 +113,7 @@ SIGNATURES = {
     "sf_head_bwd_workspace_bytes": (_sz, [C.POINTER(HeadBwdParams)]),
     "sf_head_bwd": (_i, [C.POINTER(HeadBwdParams), _f, _sz, _f]),
     "sf_add": (_i, [_f, _f, _f, _ll, _f]),
+    "sf_adam_step": (_i, [_f, _f, _f, _f, _ll, _fl, _fl, _fl, _fl, _i, _fl, _f]),
 }
 
 _lib = None
