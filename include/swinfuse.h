@@ -142,7 +142,13 @@ typedef struct {
     int shift;        /* use_cyclic_shift */
     float ln_eps;
     int precision;    /* sf_precision */
+    const void* packed; /* optional: weights pre-packed by sf_window_attn_pack (SF_PREC_BF16); NULL = pack per call */
 } sf_window_attn_params;
+/* SF_PREC_BF16 consumes the weights as bf16 tensor-core operand images.  Packing them is pure data
+ * movement that only depends on the weights, so a caller whose weights do not change between calls
+ * (inference) packs once into a buffer it owns and passes it in `packed`. */
+size_t sf_window_attn_packed_bytes(const sf_window_attn_params* p);
+int sf_window_attn_pack(const sf_window_attn_params* p, void* packed, size_t packed_bytes, void* stream);
 size_t sf_window_attn_workspace_bytes(const sf_window_attn_params* p);
 int sf_window_attn_fwd(const sf_window_attn_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -175,7 +181,10 @@ typedef struct {
     int C, hidden;
     float ln_eps;
     int precision;
+    const void* packed;     /* optional, see sf_window_attn_params.packed */
 } sf_mlp_params;
+size_t sf_mlp_packed_bytes(const sf_mlp_params* p);
+int sf_mlp_pack(const sf_mlp_params* p, void* packed, size_t packed_bytes, void* stream);
 size_t sf_mlp_workspace_bytes(const sf_mlp_params* p);
 int sf_mlp_fwd(const sf_mlp_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -203,7 +212,10 @@ typedef struct {
     int encoder;
     float ln_eps;
     int precision;
+    const void* packed;     /* optional, see sf_window_attn_params.packed */
 } sf_patch_params;
+size_t sf_patch_packed_bytes(const sf_patch_params* p);
+int sf_patch_pack(const sf_patch_params* p, void* packed, size_t packed_bytes, void* stream);
 size_t sf_patch_workspace_bytes(const sf_patch_params* p);
 int sf_patch_fwd(const sf_patch_params* p, void* workspace, size_t workspace_bytes, void* stream);
 

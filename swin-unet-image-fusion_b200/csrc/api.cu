@@ -146,6 +146,34 @@ int sf_window_attn_fwd(const sf_window_attn_params* p, void* ws, size_t ws_bytes
     if (p->precision == SF_PREC_BF16) return window_attn_fwd_bf16(p, ws, ws_bytes, as_stream(stream));
     return window_attn_fwd_f32(p, ws, ws_bytes, as_stream(stream));
 }
+size_t sf_window_attn_packed_bytes(const sf_window_attn_params* p) {
+    if (check_wa(p, "sf_window_attn_packed_bytes") != SF_OK || p->precision != SF_PREC_BF16) return 0;
+    return window_attn_packed_bytes_bf16(p);
+}
+int sf_window_attn_pack(const sf_window_attn_params* p, void* packed, size_t bytes, void* stream) {
+    SF_TRY(check_wa(p, "sf_window_attn_pack"));
+    SF_CHECK_ARG(p->precision == SF_PREC_BF16 && packed, "sf_window_attn_pack: only SF_PREC_BF16 weights are packed");
+    return window_attn_pack_bf16(p, packed, bytes, as_stream(stream));
+}
+size_t sf_mlp_packed_bytes(const sf_mlp_params* p) {
+    if (check_mlp(p, "sf_mlp_packed_bytes") != SF_OK || p->precision != SF_PREC_BF16) return 0;
+    return mlp_packed_bytes_bf16(p);
+}
+int sf_mlp_pack(const sf_mlp_params* p, void* packed, size_t bytes, void* stream) {
+    SF_TRY(check_mlp(p, "sf_mlp_pack"));
+    SF_CHECK_ARG(p->precision == SF_PREC_BF16 && packed, "sf_mlp_pack: only SF_PREC_BF16 weights are packed");
+    return mlp_pack_bf16(p, packed, bytes, as_stream(stream));
+}
+size_t sf_patch_packed_bytes(const sf_patch_params* p) {
+    if (check_patch(p, "sf_patch_packed_bytes") != SF_OK || p->precision != SF_PREC_BF16) return 0;
+    return patch_packed_bytes_bf16(p);
+}
+int sf_patch_pack(const sf_patch_params* p, void* packed, size_t bytes, void* stream) {
+    SF_TRY(check_patch(p, "sf_patch_pack"));
+    SF_CHECK_ARG(p->precision == SF_PREC_BF16 && packed, "sf_patch_pack: only SF_PREC_BF16 weights are packed");
+    return patch_pack_bf16(p, packed, bytes, as_stream(stream));
+}
+
 size_t sf_window_attn_bwd_workspace_bytes(const sf_window_attn_bwd_params* p) {
     if (!p || check_wa(&p->fwd, "sf_window_attn_bwd_workspace_bytes") != SF_OK) return 0;
     return window_attn_bwd_ws(p);

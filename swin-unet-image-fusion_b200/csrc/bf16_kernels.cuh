@@ -17,6 +17,13 @@ int mlp_fwd_bf16(const sf_mlp_params* p, void* ws, size_t ws_bytes, cudaStream_t
 size_t patch_ws_bf16(const sf_patch_params* p);
 int patch_fwd_bf16(const sf_patch_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t window_attn_packed_bytes_bf16(const sf_window_attn_params* p);
+int window_attn_pack_bf16(const sf_window_attn_params* p, void* packed, size_t bytes, cudaStream_t st);
+size_t mlp_packed_bytes_bf16(const sf_mlp_params* p);
+int mlp_pack_bf16(const sf_mlp_params* p, void* packed, size_t bytes, cudaStream_t st);
+size_t patch_packed_bytes_bf16(const sf_patch_params* p);
+int patch_pack_bf16(const sf_patch_params* p, void* packed, size_t bytes, cudaStream_t st);
+
 // ---- weight packing (tc_gemm.cu) -------------------------------------------------------------------
 // Stacks up to 3 [Neach x K] fp32 matrices along N, splits rows into n_chunks of NR and columns
 // into k_chunks of KR, and writes for every (jn, jk) a bf16 UMMA operand image img[kc][r][8]
@@ -51,6 +58,7 @@ struct TcGemm {
     int Kpad, KS, n_slabs, a_nkc, NA, NS, n_groups, chunks_per_group;
 };
 void tc_gemm_pick_nchunk(int Ntot, int* NCH, int* n_chunks);
+int tc_gemm_pick_ks(int Kpad);          // k-slab width: largest of {64,48,32,16} dividing Kpad
 int tc_gemm_plan(TcGemm* p);          // needs K, a_mode, NCH, n_chunks, M
 int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st);
 
@@ -72,5 +80,10 @@ int launch_tc_mlp(const TcMlp& t, cudaStream_t st);
 // o_nkc == 0: O row-major [Mtok][ldo]; else O in the UMMA-tiled layout with o_nkc k-chunks per tile
 int launch_attn_core_bf16(const bf16* qkv, int qkv_fp16, long long ld, int koff, int voff, bf16* O, long long ldo, int o_nkc,
                           const float* table, const WinGeom& g, int nh, int d, cudaStream_t st);
+
+// tensor-core (HMMA) attention core for 7x7 windows, fp16 q/k/v, UMMA-tiled bf16 O (attn_mma.cu);
+// returns SF_ERR_UNSUPPORTED for shapes it does not cover
+int launch_attn_core_mma(const bf16* qkv_fp16, long long ld, int koff, int voff, bf16* O, int o_nkc, const float* table,
+                         const WinGeom& g, int nh, int d, cudaStream_t st);
 
 }  // namespace sf

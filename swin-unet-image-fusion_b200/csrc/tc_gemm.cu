@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
 // host side
 // =============================================================================================
 // k-slab width: the largest of {64, 48, 32, 16} dividing Kpad
-static int pick_ks(int Kpad) {
+int tc_gemm_pick_ks(int Kpad) {
     for (int ks : {64, 48, 32, 16})
         if (Kpad % ks == 0) return ks;
     return 16;
@@ -513,7 +513,7 @@ void tc_gemm_pick_nchunk(int Ntot, int* NCH, int* n_chunks) {
 
 int tc_gemm_plan(TcGemm* p) {
     p->Kpad = (int)pad16((uint32_t)p->K);
-    p->KS = pick_ks(p->Kpad);
+    p->KS = tc_gemm_pick_ks(p->Kpad);
     p->n_slabs = p->Kpad / p->KS;
     const bool stream = p->a_mode == AM_TILED;
     SF_CHECK_ARG(p->NCH % 16 == 0 && p->NCH >= 16 && p->NCH <= 256, "tc_gemm: bad n-chunk %d", p->NCH);

@@ -27,7 +27,7 @@ class WindowAttnParams(C.Structure):
         "q_src", "kv_src", "residual", "out", "ln_q_gamma", "ln_q_beta", "ln_kv_gamma", "ln_kv_beta",
         "wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "bias_table")] + [
         (n, C.c_int) for n in ("B", "Hp", "Wp", "C", "num_heads", "head_dim", "wsh", "wsw", "shift")] + [
-        ("ln_eps", C.c_float), ("precision", C.c_int)]
+        ("ln_eps", C.c_float), ("precision", C.c_int), ("packed", _f)]
 
 
 class WindowAttnBwdParams(C.Structure):
@@ -38,7 +38,8 @@ class WindowAttnBwdParams(C.Structure):
 
 class MlpParams(C.Structure):
     _fields_ = [(n, _f) for n in ("in_", "residual", "out", "ln_gamma", "ln_beta", "w1", "b1", "w2", "b2")] + [
-        ("M", C.c_longlong), ("C", C.c_int), ("hidden", C.c_int), ("ln_eps", C.c_float), ("precision", C.c_int)]
+        ("M", C.c_longlong), ("C", C.c_int), ("hidden", C.c_int), ("ln_eps", C.c_float), ("precision", C.c_int),
+        ("packed", _f)]
 
 
 class MlpBwdParams(C.Structure):
@@ -49,7 +50,7 @@ class MlpBwdParams(C.Structure):
 class PatchParams(C.Structure):
     _fields_ = [(n, _f) for n in ("in_", "out", "w", "b", "ln_gamma", "ln_beta")] + [
         (n, C.c_int) for n in ("B", "H", "W", "Cin", "Cout", "mh", "mw", "encoder")] + [
-        ("ln_eps", C.c_float), ("precision", C.c_int)]
+        ("ln_eps", C.c_float), ("precision", C.c_int), ("packed", _f)]
 
 
 class PatchBwdParams(C.Structure):
@@ -98,6 +99,12 @@ SIGNATURES = {
     "sf_layernorm": (_i, [_f, _f, _f, _f, _ll, _i, _fl, _i, _f]),
     "sf_window_attn_workspace_bytes": (_sz, [C.POINTER(WindowAttnParams)]),
     "sf_window_attn_fwd": (_i, [C.POINTER(WindowAttnParams), _f, _sz, _f]),
+    "sf_window_attn_packed_bytes": (_sz, [C.POINTER(WindowAttnParams)]),
+    "sf_window_attn_pack": (_i, [C.POINTER(WindowAttnParams), _f, _sz, _f]),
+    "sf_mlp_packed_bytes": (_sz, [C.POINTER(MlpParams)]),
+    "sf_mlp_pack": (_i, [C.POINTER(MlpParams), _f, _sz, _f]),
+    "sf_patch_packed_bytes": (_sz, [C.POINTER(PatchParams)]),
+    "sf_patch_pack": (_i, [C.POINTER(PatchParams), _f, _sz, _f]),
     "sf_window_attn_bwd_workspace_bytes": (_sz, [C.POINTER(WindowAttnBwdParams)]),
     "sf_window_attn_bwd": (_i, [C.POINTER(WindowAttnBwdParams), _f, _sz, _f]),
     "sf_mlp_workspace_bytes": (_sz, [C.POINTER(MlpParams)]),

@@ -84,6 +84,37 @@ def to_nchw_contiguous(x: Tensor) -> Tensor:
     return _NhwcToNchw.apply(x)
 
 
+_weights_epoch = 0
+
+
+def invalidate_packed_cache() -> None:
+    """Call after weights were modified behind autograd's back (e.g. by sf_adam_step writing through
+    raw pointers): in-place torch ops bump ``_version`` and are detected automatically."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def _packed_weights(holder, key_tensors, nbytes_fn, pack_fn, p, like: Tensor, what: str):
+    """bf16 tensor-core operand images of the weights: packed once per weight version, owned by the
+    caller side (stored on the parameter object), passed to the library through ``params.packed``."""
+    if p.precision != SF_PREC_BF16 or holder is None:
+        return None
+    key = (_weights_epoch, tuple((t.data_ptr(), t._version) for t in key_tensors if t is not None))
+    cached = getattr(holder, "_sf_packed", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    nbytes = nbytes_fn(C.byref(p))
+    if nbytes == 0:
+        return None
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=like.device)
+    check(pack_fn(C.byref(p), buf.data_ptr(), nbytes, _stream()), what)
+    try:
+        holder._sf_packed = (key, buf)
+    except AttributeError:
+        pass
+    return buf
+
+
 def _workspace(nbytes: int, like: Tensor) -> Tuple[Optional[Tensor], Optional[int]]:
     if nbytes == 0:
         return None, None
@@ -315,6 +346,9 @@ class _WindowAttn(torch.autograd.Function):
         tens = [_param(t, n) for n, t in zip(_WA_TENSORS, tensors)]
         p = _lib.WindowAttnParams()
         _fill_wa(p, q, kv_t, residual, out, tens, cfg)
+        packed = _packed_weights(tensors[4], tens[4:12], lib.sf_window_attn_packed_bytes, lib.sf_window_attn_pack, p, q,
+                                 "sf_window_attn_pack")
+        p.packed = _ptr(packed)
         nbytes = lib.sf_window_attn_workspace_bytes(C.byref(p))
         ws, wsp = _workspace(nbytes, q)
         check(lib.sf_window_attn_fwd(C.byref(p), wsp, nbytes, _stream()), "sf_window_attn_fwd")
@@ -396,6 +430,8 @@ class _Mlp(torch.autograd.Function):
         tens = [_param(t, n) for n, t in zip(_MLP_TENSORS, (ln_g, ln_b, w1, b1, w2, b2))]
         p = _lib.MlpParams()
         _fill_mlp(p, x, residual, out, tens, eps, prec)
+        packed = _packed_weights(w1, tens[2:6], lib.sf_mlp_packed_bytes, lib.sf_mlp_pack, p, x, "sf_mlp_pack")
+        p.packed = _ptr(packed)
         nbytes = lib.sf_mlp_workspace_bytes(C.byref(p))
         ws, wsp = _workspace(nbytes, x)
         check(lib.sf_mlp_fwd(C.byref(p), wsp, nbytes, _stream()), "sf_mlp_fwd")
@@ -459,6 +495,8 @@ class _Patch(torch.autograd.Function):
         tens = [_param(t, n) for n, t in zip(_PATCH_TENSORS, (w, bias, ln_g, ln_b))]
         p = _lib.PatchParams()
         _fill_patch(p, x, out, tens, encoder, ms, cout, eps, prec)
+        packed = _packed_weights(w, tens[0:2], lib.sf_patch_packed_bytes, lib.sf_patch_pack, p, x, "sf_patch_pack")
+        p.packed = _ptr(packed)
         nbytes = lib.sf_patch_workspace_bytes(C.byref(p))
         ws, wsp = _workspace(nbytes, x)
         check(lib.sf_patch_fwd(C.byref(p), wsp, nbytes, _stream()), "sf_patch_fwd")

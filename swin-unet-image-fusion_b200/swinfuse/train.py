@@ -87,6 +87,8 @@ class FlatAdam:
                                            self.exp_avg_sq.data_ptr(), f.numel, self.lr, self.betas[0], self.betas[1],
                                            self.eps, self.step_count, grad_scale, torch.cuda.current_stream().cuda_stream),
                    "sf_adam_step")
+        from . import ops
+        ops.invalidate_packed_cache()   # the kernel wrote the weights through raw pointers
 
 
 class DataParallelTrainer:

@@ -41,7 +41,7 @@ def test_struct_layouts_match_header_field_order():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(float|int|long long|size_t)\s*\*?", "", decl)
+            decl = re.sub(r"^(const\s+)?(float|int|long long|size_t|void)\s*\*?", "", decl)
             names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
         mine = [n.rstrip("_") for n, _ in struct._fields_]
         assert names == mine, (cname, names, mine)
