@@ -206,10 +206,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     with torch.no_grad(), torch.cuda.stream(stream):
         # ---- eager warm-up (also the first-call module checks) + launch count per forward ---------
+        d_out = model(d_ir, d_vis)           # first call: one-time weight packing, module input checks
         ops.reset_launch_count()
         d_out = model(d_ir, d_vis)
-        launches_per_fwd = ops.launch_count()
-        for _ in range(max(0, args.warmup - 1)):
+        launches_per_fwd = ops.launch_count()   # steady-state kernels per forward (what the CUDA graph replays)
+        for _ in range(max(0, args.warmup - 2)):
             d_out = model(d_ir, d_vis)
         stream.synchronize()
 

@@ -61,6 +61,9 @@ void tc_gemm_pick_nchunk(int Ntot, int* NCH, int* n_chunks);
 int tc_gemm_pick_ks(int Kpad);          // k-slab width: largest of {64,48,32,16} dividing Kpad
 int tc_gemm_plan(TcGemm* p);          // needs K, a_mode, NCH, n_chunks, M
 int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st);
+// fp32 rows -> LayerNorm -> bf16 UMMA-tiled (pre-pass for wide rows, see tc_gemm.cu)
+int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st);
+static constexpr int TC_LN_PREPASS_MIN_C = 96;   // rows at least this wide are normalised by the pre-pass
 
 // ---- fused small-channel MLP (tc_mlp.cu) -------------------------------------------------------------
 struct TcMlp {

@@ -48,7 +48,8 @@ struct WaPlan {
     int inner;
     PackedGemm q, kv, o;          // q: stacked q|k|v for self attention
     size_t packed_bytes;
-    size_t off_qkv, off_o, off_packed, total;   // workspace
+    bool prepass_q, prepass_kv;
+    size_t off_qkv, off_o, off_packed, off_nq, off_nkv, total;   // workspace
 };
 
 static WaPlan wa_plan(const sf_window_attn_params* p) {
@@ -65,6 +66,10 @@ static WaPlan wa_plan(const sf_window_attn_params* p) {
     w.off_qkv = c.take((size_t)M * 3 * w.inner * sizeof(bf16));
     w.off_o = c.take(tiled_elems(M, w.inner) * sizeof(bf16));
     w.off_packed = c.take(p->packed ? 0 : w.packed_bytes);
+    w.prepass_q = p->ln_q_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
+    w.prepass_kv = !w.self_attn && p->ln_kv_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
+    w.off_nq = c.take(w.prepass_q ? tiled_elems(M, p->C) * sizeof(bf16) : 0);
+    w.off_nkv = c.take(w.prepass_kv ? tiled_elems(M, p->C) * sizeof(bf16) : 0);
     w.total = c.off;
     return w;
 }
@@ -123,6 +128,11 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
     g.A = p->q_src; g.ln_g = p->ln_q_gamma; g.ln_b = p->ln_q_beta; g.a_mode = p->ln_q_gamma ? AM_F32_LN : AM_F32;
     bind_packed(g, w.q, pk);
     g.out_col0 = 0; g.N = w.self_attn ? 3 * inner : inner;
+    if (w.prepass_q) {   // wide rows: LayerNorm once into the UMMA-tiled layout, GEMM streams it
+        bf16* nq = reinterpret_cast<bf16*>(base + w.off_nq);
+        SF_TRY(launch_ln_to_tiled(p->q_src, p->ln_q_gamma, p->ln_q_beta, nq, M, C, p->ln_eps, st));
+        g.A = nq; g.a_mode = AM_TILED;
+    }
     SF_TRY(tc_gemm_plan(&g));
     SF_TRY(launch_tc_gemm(g, prof_name(w.self_attn ? "tc_gemm_qkv_c%d" : "tc_gemm_q_c%d", C), st));
     if (!w.self_attn) {
@@ -130,6 +140,11 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
         k.A = p->kv_src; k.ln_g = p->ln_kv_gamma; k.ln_b = p->ln_kv_beta; k.a_mode = p->ln_kv_gamma ? AM_F32_LN : AM_F32;
         bind_packed(k, w.kv, pk);
         k.out_col0 = inner; k.N = 2 * inner;
+        if (w.prepass_kv) {
+            bf16* nkv = reinterpret_cast<bf16*>(base + w.off_nkv);
+            SF_TRY(launch_ln_to_tiled(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, nkv, M, C, p->ln_eps, st));
+            k.A = nkv; k.a_mode = AM_TILED;
+        }
         SF_TRY(tc_gemm_plan(&k));
         SF_TRY(launch_tc_gemm(k, prof_name("tc_gemm_kv_c%d", C), st));
     }
@@ -155,7 +170,7 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
 // MLP: GEMM1 (LN, +b1, ELU, bf16 UMMA-tiled hidden) + GEMM2 (bulk-copied A, +b2 +residual).
 // (tc_mlp.cu holds a fused single-kernel variant; see DESIGN.md for why it is not dispatched yet.)
 // =============================================================================================
-struct MlpPlan { PackedGemm g1, g2; size_t packed_bytes, off_h, off_packed, total; };
+struct MlpPlan { PackedGemm g1, g2; bool prepass; size_t packed_bytes, off_h, off_packed, off_n, total; };
 
 static MlpPlan mlp_plan(const sf_mlp_params* p) {
     MlpPlan m{};
@@ -166,6 +181,8 @@ static MlpPlan mlp_plan(const sf_mlp_params* p) {
     Carver c;
     m.off_h = c.take(tiled_elems(p->M, p->hidden) * sizeof(bf16));
     m.off_packed = c.take(p->packed ? 0 : m.packed_bytes);
+    m.prepass = p->ln_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
+    m.off_n = c.take(m.prepass ? tiled_elems(p->M, p->C) * sizeof(bf16) : 0);
     m.total = c.off;
     return m;
 }
@@ -210,6 +227,11 @@ int mlp_fwd_bf16(const sf_mlp_params* p, void* ws_ptr, size_t ws_bytes, cudaStre
     bind_packed(g1, m.g1, pk);
     g1.elu = 1;
     g1.out = hid; g1.N = p->hidden; g1.out_nkc = (int)pad16((uint32_t)p->hidden) / 8;
+    if (m.prepass) {
+        bf16* nb = reinterpret_cast<bf16*>(base + m.off_n);
+        SF_TRY(launch_ln_to_tiled(p->in, p->ln_gamma, p->ln_beta, nb, p->M, p->C, p->ln_eps, st));
+        g1.A = nb; g1.a_mode = AM_TILED;
+    }
     SF_TRY(tc_gemm_plan(&g1));
     SF_TRY(launch_tc_gemm(g1, prof_name("tc_gemm_mlp1_c%d", p->C), st));
     TcGemm g2{};

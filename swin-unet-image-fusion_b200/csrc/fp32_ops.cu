@@ -48,6 +48,82 @@ __global__ void k_ln_rows(const float* __restrict__ in, const float* __restrict_
     }
 }
 
+
+// Short rows (C <= 64, C % 4 == 0): one thread per row, the row in registers (float4 loads, no
+// shuffles) -- the warp-per-row kernel above leaves most lanes idle there (C = 4 or 24).
+template <bool ACT, bool UNMERGE, int NF4>
+__global__ void k_ln_rows_small(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float* __restrict__ out, long long M, int C, float eps, UnmergeGeom ug) {
+    const int nf4 = C >> 2;
+    for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < M; row += (long long)gridDim.x * blockDim.x) {
+        float4 v[NF4];
+        const float4* src = reinterpret_cast<const float4*>(in + row * C);
+#pragma unroll
+        for (int i = 0; i < NF4; i++) v[i] = i < nf4 ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NF4; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float mean = s / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NF4; i++) {
+            if (i < nf4) {
+                float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+        const float rstd = rsqrtf(q / (float)C + eps);
+        long long obase = row * C;
+        int Cout = C, ostride = 0, Wf = 0;
+        if (UNMERGE) {
+            int X = (int)(row % ug.Wc);
+            long long p = row / ug.Wc;
+            int Y = (int)(p % ug.Hc);
+            long long b = p / ug.Hc;
+            Wf = ug.Wc * ug.mw;
+            obase = ((b * (ug.Hc * ug.mh) + (long long)Y * ug.mh) * Wf + (long long)X * ug.mw) * ug.Cout;
+            Cout = ug.Cout;
+            ostride = 1;
+        }
+#pragma unroll
+        for (int i = 0; i < NF4; i++) {
+            if (i < nf4) {
+                float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i), bb = __ldg(reinterpret_cast<const float4*>(beta) + i);
+                float y[4] = {(v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                              (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) if (ACT) y[e] = elu1(y[e]);
+                if (!ostride) {
+                    *reinterpret_cast<float4*>(out + obase + i * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                } else {
+                    // channel c = q*Cout + ch -> fine pixel (ph, pw) = (q / mw, q % mw), channel ch
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        int c = i * 4 + e, qq = c / Cout, ch = c - qq * Cout;
+                        int ph = qq / ug.mw, pw = qq - ph * ug.mw;
+                        out[obase + ((long long)ph * Wf + pw) * Cout + ch] = y[e];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NF4>
+static void launch_ln_small(const float* in, const float* gamma, const float* beta, float* out, long long M, int C, float eps,
+                            int act, const UnmergeGeom* ug, cudaStream_t st) {
+    long long blocks = (M + 127) / 128;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    UnmergeGeom g = ug ? *ug : UnmergeGeom{0, 0, 0, 0, 0};
+    if (ug) {
+        if (act) k_ln_rows_small<true, true, NF4><<<(int)blocks, 128, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+        else k_ln_rows_small<false, true, NF4><<<(int)blocks, 128, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+    } else {
+        if (act) k_ln_rows_small<true, false, NF4><<<(int)blocks, 128, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+        else k_ln_rows_small<false, false, NF4><<<(int)blocks, 128, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+    }
+}
+
 int launch_layernorm(const float* in, const float* gamma, const float* beta, float* out, long long M, int C, float eps,
                      int act, const UnmergeGeom* ug, cudaStream_t st) {
     const int threads = 256;
@@ -56,6 +132,15 @@ int launch_layernorm(const float* in, const float* gamma, const float* beta, flo
     if (blocks < 1) blocks = 1;
     UnmergeGeom g = ug ? *ug : UnmergeGeom{0, 0, 0, 0, 0};
     ProfScope ps(act ? "layernorm_elu" : "layernorm", 8.0 * (double)M * C, 8.0 * (double)M * C, st);
+    const bool al = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    if (C % 4 == 0 && C <= 64 && al && M > 0) {
+        if (C <= 16) launch_ln_small<4>(in, gamma, beta, out, M, C, eps, act, ug, st);
+        else if (C <= 32) launch_ln_small<8>(in, gamma, beta, out, M, C, eps, act, ug, st);
+        else launch_ln_small<16>(in, gamma, beta, out, M, C, eps, act, ug, st);
+        SF_CHECK_LAUNCH("layernorm_small");
+        return SF_OK;
+    }
     if (ug) {
         if (act) k_ln_rows<true, true><<<(int)blocks, threads, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
         else k_ln_rows<false, true><<<(int)blocks, threads, 0, st>>>(in, gamma, beta, out, M, C, eps, g);

@@ -264,6 +264,72 @@ __device__ __forceinline__ void produce_a_merge(uint8_t* sA, const TcGemm& p, lo
     }
 }
 
+
+// =============================================================================================
+// LayerNorm pre-pass for wide rows: fp32 rows -> LN -> bf16 in the UMMA-tiled layout, so that the
+// GEMMs consuming it run in the STREAM flavour (A arrives by bulk copy, no producer warps in the
+// critical path and no per-n-group recomputation of the LayerNorm).  One warp per row.
+// =============================================================================================
+__global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              bf16* __restrict__ out, long long M, int C, int Kpad, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int nf4 = C >> 2, nslots = Kpad >> 2, nkc = Kpad >> 3;
+    long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (; row < M; row += stride) {
+        float4 v[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            int q = lane + 32 * i;
+            v[i] = q < nf4 ? *reinterpret_cast<const float4*>(in + row * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)C;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (lane + 32 * i < nf4) {
+                float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float rstd = rsqrtf(ss / (float)C + eps);
+        const long long tile = row >> 7;
+        const int r = (int)(row & 127);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            int q = lane + 32 * i;
+            if (q < nslots) {
+                uint2 pk = make_uint2(0u, 0u);
+                if (q < nf4) {
+                    float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + q), bb = __ldg(reinterpret_cast<const float4*>(beta) + q);
+                    pk = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
+                                    pack_bf16x2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w));
+                }
+                *reinterpret_cast<uint2*>(out + ((tile * nkc + (q >> 1)) * 128 + r) * 8 + (q & 1) * 4) = pk;
+            }
+        }
+    }
+}
+
+int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st) {
+    const int Kpad = (int)pad16((uint32_t)C);
+    SF_CHECK_ARG(C % 4 == 0 && Kpad <= TC_MAX_KPAD, "ln_to_tiled: unsupported row width %d", C);
+    long long blocks = (M * 32 + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (blocks < 1) blocks = 1;
+    ProfScope ps(prof_name("ln_to_tiled_c%d", C), 8.0 * (double)M * C, 6.0 * (double)M * C, st);
+    k_ln_to_tiled<<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps);
+    SF_CHECK_LAUNCH("ln_to_tiled");
+    return SF_OK;
+}
+
 // =============================================================================================
 // the kernel
 // =============================================================================================
@@ -574,6 +640,8 @@ int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st) {
     if (p.a_mode == AM_F32_LN && p.out_mode == OUT_TILED) return launch_t<AM_F32_LN, OUT_TILED>(p, name, st);
     if (p.a_mode == AM_F32 && p.out_mode == OUT_TILED) return launch_t<AM_F32, OUT_TILED>(p, name, st);
     if (p.a_mode == AM_TILED && p.out_mode == OUT_F32) return launch_t<AM_TILED, OUT_F32>(p, name, st);
+    if (p.a_mode == AM_TILED && p.out_mode == OUT_BF16) return launch_t<AM_TILED, OUT_BF16>(p, name, st);
+    if (p.a_mode == AM_TILED && p.out_mode == OUT_TILED) return launch_t<AM_TILED, OUT_TILED>(p, name, st);
     if (p.a_mode == AM_F32 && p.out_mode == OUT_F32) return launch_t<AM_F32, OUT_F32>(p, name, st);
     if (p.a_mode == AM_MERGE && p.out_mode == OUT_F32) return launch_t<AM_MERGE, OUT_F32>(p, name, st);
     set_error("tc_gemm: unsupported mode combination (%d -> %d)", p.a_mode, p.out_mode);
