@@ -13,9 +13,11 @@
 //                   tiles' global loads are in flight); idle in the STREAM flavour
 //   warp  8    MMA issuer         one lane issues tcgen05.mma, commits to mbarriers
 //   warp  9    loader             one lane drives cp.async.bulk for weight (and A) k-slabs
-//   warps 10-13 epilogue          tcgen05.ld -> registers -> global
+//   warps 10-17 epilogue          tcgen05.ld -> registers -> global; two warps per TMEM lane quarter, each
+//                                 taking every other 16-column group (the epilogue is the longest stage)
 // Pipelines: A buffers (full/empty), k-slab ring (full/empty), two TMEM accumulators (full/empty),
 // so the producers work on item i+1 and the epilogue on chunk j-1 while the tensor core runs chunk j.
+#include <algorithm>
 #include <initializer_list>
 #include "bf16_kernels.cuh"
 #include "tc_common.cuh"
@@ -24,7 +26,8 @@ namespace sf {
 using namespace tc;
 
 static constexpr uint32_t SBO = 128;
-static constexpr int G_THREADS = 448;
+static constexpr int G_THREADS = 576;          // RESIDENT flavour: 8 producer + MMA + loader + 8 epilogue warps
+static constexpr int G_THREADS_STREAM = 320;   // STREAM flavour: no producer warps
 static constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 __host__ __device__ static inline uint32_t align128(uint32_t v) { return (v + 127) & ~127u; }
@@ -353,10 +356,11 @@ __host__ __device__ static inline GemmSmem gemm_smem_layout(const TcGemm& p) {
 }
 
 template <int AMODE, int OUTMODE>
-__global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
+__global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREADS, 1) k_tc_gemm2(TcGemm p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr bool STREAM = (AMODE == AM_TILED);
+    constexpr int PW = STREAM ? 0 : 8;          // producer warps; roles after them: MMA, loader, 8 epilogue warps
     const GemmSmem L = gemm_smem_layout(p);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* a_full = bars;            // [2]
@@ -372,18 +376,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
     const long long m_tiles = (p.M + 127) / 128;
     const long long items = m_tiles * p.n_groups;
 
-    if (tid == 256) {  // warp 8 lane 0
-        for (int i = 0; i < 2; i++) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+    if (tid == PW * 32) {  // MMA warp, lane 0
+        for (int i = 0; i < 2; i++) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8); }
         for (int i = 0; i < NS; i++) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, ncols);
+    if (warp == PW + 1) tmem_alloc(tmem_slot, ncols);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < PW) {
         // ------------------------------ A producers -------------------------------------------------
         const uint32_t grp = (uint32_t)warp >> 2;
         const int ptid = tid & 127;
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
                 mbar_arrive(&a_full[ab]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == PW) {
         // ------------------------------ MMA issuer ----------------------------------------------------
         if (lane == 0) {
             uint32_t acount = 0, wit = 0, tcount = 0;
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
                 if (!STREAM) umma_commit(&a_empty[ab]);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == PW + 1) {
         // ------------------------------ loader (bulk-copy engine) --------------------------------------
         if (lane == 0) {
             uint32_t wit = 0;
@@ -468,7 +472,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
         }
     } else {
         // ------------------------------ epilogue ---------------------------------------------------------
-        const int rb = warp & 3;                 // TMEM lane quarter this warp may access
+        const int rb = warp & 3;                 // TMEM lane quarter this warp may access (hardware: warp id % 4)
+        const int eg = (warp - (PW + 2)) >> 2;    // which half of the 16-column groups
         const int row = rb * 32 + lane;
         uint32_t tcount = 0;
         for (long long item = blockIdx.x; item < items; item += gridDim.x) {
@@ -484,9 +489,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
                 tc_fence_after_sync();
                 const uint32_t tlane = tmem_base + acc * acc_stride + ((uint32_t)(rb * 32) << 16);
                 const int ncol0 = c * p.NCH;
-                for (int c16 = 0; c16 < p.NCH; c16 += 16) {
+                for (int c16 = eg * 16; c16 < p.NCH; c16 += 32) {
                     const int n0 = ncol0 + c16;
-                    if (n0 >= p.N) break;  // uniform
+                    if (n0 >= p.N) break;  // uniform per warp
                     float v[16];
                     tmem_ld16(tlane + (uint32_t)c16, v);
                     if (m < p.M) {
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_gemm2(TcGemm p) {
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, ncols);
+    if (warp == PW + 1) tmem_dealloc(tmem_base, ncols);
 }
 
 // =============================================================================================
@@ -623,13 +628,17 @@ static int launch_t(const TcGemm& p, const char* name, cudaStream_t st) {
     const long long m_tiles = (p.M + 127) / 128;
     const long long items = m_tiles * p.n_groups;
     const uint32_t ncols = tmem_cols_pow2(2u * (((uint32_t)p.NCH + 31u) & ~31u));
-    int per_sm = (L.total * 2 + 2048 <= SMEM_LIMIT && ncols <= 256) ? 2 : 1;
+    const int threads = AMODE == AM_TILED ? G_THREADS_STREAM : G_THREADS;
+    int per_sm = (int)(SMEM_LIMIT / (L.total + 1024));
+    per_sm = std::min(per_sm, (int)(512u / ncols));
+    per_sm = std::min(per_sm, 65536 / (threads * (AMODE == AM_TILED ? 66 : 100)));
+    per_sm = std::max(1, std::min(per_sm, 4));
     long long grid = 148LL * per_sm;
     if (grid > items) grid = items;
     const double abytes = (AMODE == AM_TILED ? 2.0 : 4.0) * (double)p.M * p.K;
     const double obytes = (OUTMODE == OUT_F32 ? 4.0 : 2.0) * (double)p.M * p.N + (p.residual ? 4.0 * (double)p.M * p.N : 0.0);
     ProfScope ps(name, 2.0 * (double)p.M * p.N * p.K, abytes + obytes + 2.0 * (double)p.N * p.K, st);
-    k_tc_gemm2<AMODE, OUTMODE><<<(unsigned)grid, G_THREADS, L.total, st>>>(p);
+    k_tc_gemm2<AMODE, OUTMODE><<<(unsigned)grid, threads, L.total, st>>>(p);
     SF_CHECK_LAUNCH("tc_gemm");
     return SF_OK;
 }
