@@ -31,6 +31,7 @@ static constexpr int AM_THREADS = 256;
 
 struct AttnMmaArgs {
     const __half* qkv; long long ld; int koff, voff;
+    int qkv_nkc;                     // > 0: qkv is UMMA-tiled ([tile][chunk][row][8]) with this many chunks per tile; 0: rows of ld halves
     bf16* O; int o_nkc;              // UMMA-tiled output, o_nkc k-chunks per 128-token tile
     const float* table;
     WinGeom g;
@@ -52,6 +53,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ const __half* qkv_chunk_ptr(const AttnMmaArgs& a, long long tok, int col) {
+    if (a.qkv_nkc == 0) return a.qkv + tok * a.ld + col;
+    return a.qkv + (((tok >> 7) * a.qkv_nkc + (col >> 3)) * 128 + (tok & 127)) * 8 + (col & 7);
 }
 
 template <int KSTEPS, int NDT>
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(AM_THREADS, (KSTEPS == 1 && NDT <= 2) ? 3 : 1)
     const int slab = warp & 3;
     const int r0 = slab * 16 + gq, r1 = r0 + 8;
     const __half2 qscale = __float2half2_rn(a.scale_log2e);
-    const bool vec_in = ((inner & 7) == 0) && ((a.ld & 7) == 0) && ((a.koff & 7) == 0) && ((a.voff & 7) == 0);
+    const bool vec_in = ((inner & 7) == 0) && (a.qkv_nkc != 0 || (a.ld & 7) == 0) && ((a.koff & 7) == 0) && ((a.voff & 7) == 0);
     const int nch = inner >> 3;
     const int nchunks = MT * 3 * nch;
     const int nWimg = g.nWh * g.nWw;
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(AM_THREADS, (KSTEPS == 1 && NDT <= 2) ? 3 : 1)
 #pragma unroll
         for (int k = 0; k < 2; k++)
             if (tid + k * AM_THREADS < nchunks)
-                raw[k] = *reinterpret_cast<const uint4*>(a.qkv + src_row(b, wh, ww, p_tok[k]) * a.ld + p_col[k]);
+                raw[k] = *reinterpret_cast<const uint4*>(qkv_chunk_ptr(a, src_row(b, wh, ww, p_tok[k]), p_col[k]));
     };
     prefetch(blockIdx.x);
 
@@ -188,16 +194,16 @@ __global__ void __launch_bounds__(AM_THREADS, (KSTEPS == 1 && NDT <= 2) ? 3 : 1)
             for (int i = tid + 2 * AM_THREADS; i < nchunks; i += AM_THREADS) {
                 int tok, which, col, idx, dd;
                 decode(i, tok, which, col, idx, dd);
-                uint4 r = *reinterpret_cast<const uint4*>(a.qkv + src_row(wb, wwh, www, tok) * a.ld + col);
+                uint4 r = *reinterpret_cast<const uint4*>(qkv_chunk_ptr(a, src_row(wb, wwh, www, tok), col));
                 scatter(r, which, idx, dd);
             }
         } else {
             for (int i = tid; i < MT * inner; i += AM_THREADS) {
                 int t = i / inner, cc = i - t * inner, h = cc / d, dd = cc - h * d;
-                const __half* src = a.qkv + src_row(wb, wwh, www, t) * a.ld + cc;
-                Qs[((size_t)h * MROWS + t) * DS + dd] = __hmul(src[0], __low2half(qscale));
-                Ks[((size_t)h * MKEYS + t) * DS + dd] = src[a.koff];
-                Vt[((size_t)h * DV + dd) * VS + t] = src[a.voff];
+                const long long tokr = src_row(wb, wwh, www, t);
+                Qs[((size_t)h * MROWS + t) * DS + dd] = __hmul(*qkv_chunk_ptr(a, tokr, cc), __low2half(qscale));
+                Ks[((size_t)h * MKEYS + t) * DS + dd] = *qkv_chunk_ptr(a, tokr, a.koff + cc);
+                Vt[((size_t)h * DV + dd) * VS + t] = *qkv_chunk_ptr(a, tokr, a.voff + cc);
             }
         }
         __syncthreads();
@@ -336,13 +342,15 @@ static int launch_attn_mma_t(const AttnMmaArgs& a, cudaStream_t st) {
     return SF_OK;
 }
 
+bool attn_mma_supported(const WinGeom& g, int d) { return g.T == MT && g.wsh == 7 && g.wsw == 7 && d <= 48; }
+
 // returns SF_ERR_UNSUPPORTED (without setting an error) when the shape is not covered: the caller
 // then uses the CUDA-core kernels of attn_core.cu
-int launch_attn_core_mma(const bf16* qkv_fp16, long long ld, int koff, int voff, bf16* O, int o_nkc, const float* table,
+int launch_attn_core_mma(const bf16* qkv_fp16, long long ld, int qkv_nkc, int koff, int voff, bf16* O, int o_nkc, const float* table,
                          const WinGeom& g, int nh, int d, cudaStream_t st) {
     if (!(g.T == MT && g.wsh == 7 && g.wsw == 7 && o_nkc > 0 && d <= 48)) return SF_ERR_UNSUPPORTED;
     AttnMmaArgs a{};
-    a.qkv = reinterpret_cast<const __half*>(qkv_fp16); a.ld = ld; a.koff = koff; a.voff = voff; a.O = O; a.o_nkc = o_nkc;
+    a.qkv = reinterpret_cast<const __half*>(qkv_fp16); a.ld = ld; a.qkv_nkc = qkv_nkc; a.koff = koff; a.voff = voff; a.O = O; a.o_nkc = o_nkc;
     a.table = table; a.g = g; a.nh = nh; a.d = d;
     a.nwin = (long long)g.B * g.nWh * g.nWw;
     a.scale_log2e = 1.4426950408889634f / sqrtf((float)d);

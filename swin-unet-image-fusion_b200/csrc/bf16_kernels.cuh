@@ -85,8 +85,10 @@ int launch_attn_core_bf16(const bf16* qkv, int qkv_fp16, long long ld, int koff,
                           const float* table, const WinGeom& g, int nh, int d, cudaStream_t st);
 
 // tensor-core (HMMA) attention core for 7x7 windows, fp16 q/k/v, UMMA-tiled bf16 O (attn_mma.cu);
-// returns SF_ERR_UNSUPPORTED for shapes it does not cover
-int launch_attn_core_mma(const bf16* qkv_fp16, long long ld, int koff, int voff, bf16* O, int o_nkc, const float* table,
+// returns SF_ERR_UNSUPPORTED for shapes it does not cover (attn_mma_supported tells in advance);
+// qkv_nkc > 0: q/k/v are stored UMMA-tiled with that many 8-column chunks per 128-token tile
+bool attn_mma_supported(const WinGeom& g, int d);
+int launch_attn_core_mma(const bf16* qkv_fp16, long long ld, int qkv_nkc, int koff, int voff, bf16* O, int o_nkc, const float* table,
                          const WinGeom& g, int nh, int d, cudaStream_t st);
 
 }  // namespace sf

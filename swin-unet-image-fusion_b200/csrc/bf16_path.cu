@@ -63,7 +63,7 @@ static WaPlan wa_plan(const sf_window_attn_params* p) {
     w.o = plan_packed(pc, p->C, w.inner);
     w.packed_bytes = pc.off;
     Carver c;
-    w.off_qkv = c.take((size_t)M * 3 * w.inner * sizeof(bf16));
+    w.off_qkv = c.take(tiled_elems(M, 3 * w.inner) * sizeof(bf16));   // rows or UMMA-tiled (padded), see fwd
     w.off_o = c.take(tiled_elems(M, w.inner) * sizeof(bf16));
     w.off_packed = c.take(p->packed ? 0 : w.packed_bytes);
     w.prepass_q = p->ln_q_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
@@ -121,10 +121,15 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
         SF_TRY(window_attn_pack_bf16(p, base + w.off_packed, w.packed_bytes, st));
         pk = base + w.off_packed;
     }
-    // projections -> qkv [M][3*inner] fp16 rows
+    // projections -> q|k|v, fp16.  With the HMMA attention core they are written UMMA-tiled
+    // ([tile][chunk][row][8]: the epilogue's 16-byte stores are contiguous across a warp) and the
+    // core gathers 16-byte chunks from it; the CUDA-core fallback reads plain rows.
+    WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
+    const bool use_mma = attn_mma_supported(geom, p->head_dim) && inner % 8 == 0;
+    const int qkv_nkc = use_mma ? (int)pad16((uint32_t)(3 * inner)) / 8 : 0;
     TcGemm g{};
-    g.M = M; g.K = C; g.lda = C; g.eps = p->ln_eps; g.out_mode = OUT_BF16; g.out_fp16 = 1;
-    g.out = qkv; g.ldo = 3 * inner;
+    g.M = M; g.K = C; g.lda = C; g.eps = p->ln_eps; g.out_mode = use_mma ? OUT_TILED : OUT_BF16; g.out_fp16 = 1;
+    g.out = qkv; g.ldo = 3 * inner; g.out_nkc = qkv_nkc;
     g.A = p->q_src; g.ln_g = p->ln_q_gamma; g.ln_b = p->ln_q_beta; g.a_mode = p->ln_q_gamma ? AM_F32_LN : AM_F32;
     bind_packed(g, w.q, pk);
     g.out_col0 = 0; g.N = w.self_attn ? 3 * inner : inner;
@@ -149,11 +154,10 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
         SF_TRY(launch_tc_gemm(k, prof_name("tc_gemm_kv_c%d", C), st));
     }
     // attention core -> O (bf16, UMMA-tiled so the projection GEMM can bulk-copy it)
-    WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
     const int o_nkc = (int)pad16((uint32_t)inner) / 8;
-    int arc = launch_attn_core_mma(qkv, 3 * inner, inner, 2 * inner, O, o_nkc, p->bias_table, geom, p->num_heads, p->head_dim, st);
-    if (arc == SF_ERR_UNSUPPORTED)   // other window sizes / head dims: CUDA-core kernels
-        arc = launch_attn_core_bf16(qkv, 1, 3 * inner, inner, 2 * inner, O, 0, o_nkc, p->bias_table, geom, p->num_heads, p->head_dim, st);
+    int arc;
+    if (use_mma) arc = launch_attn_core_mma(qkv, 3 * inner, qkv_nkc, inner, 2 * inner, O, o_nkc, p->bias_table, geom, p->num_heads, p->head_dim, st);
+    else arc = launch_attn_core_bf16(qkv, 1, 3 * inner, inner, 2 * inner, O, 0, o_nkc, p->bias_table, geom, p->num_heads, p->head_dim, st);
     SF_TRY(arc);
     // output projection (+ residual) -> out fp32 rows
     TcGemm o{};

@@ -511,8 +511,10 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                             // (zero weights, zero bias, ELU(0) = 0) which is exactly the K padding the next GEMM needs
                             bf16* o = reinterpret_cast<bf16*>(p.out);
                             const int kc = (p.out_col0 + n0) >> 3;
-                            uint4 lo = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                            uint4 hi = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) pk[i] = p.out_fp16 ? pack_f16x2(v[2 * i], v[2 * i + 1]) : pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                            uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                             *reinterpret_cast<uint4*>(o + (((size_t)tile * p.out_nkc + kc) * 128 + row) * 8) = lo;
                             if (kc + 1 < p.out_nkc) *reinterpret_cast<uint4*>(o + (((size_t)tile * p.out_nkc + kc + 1) * 128 + row) * 8) = hi;
                         } else if (OUTMODE == OUT_BF16) {
