@@ -32,10 +32,27 @@ int patch_pack_bf16(const sf_patch_params* p, void* packed, size_t bytes, cudaSt
 struct PackSrc { const float* w[3]; const float* b[3]; };
 int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
                 int k_chunks, cudaStream_t st);
+// Same images, but the N axis is a concatenation of sources with their own layout: source s has
+// rows[s] packed rows; head_padded[s] != 0 means packed row n' = h*dp + dd maps to source row h*d + dd
+// (zero when dd >= d); weights and bias of source s are multiplied by scale[s].
+struct PackMap { int nsrc; int rows[3]; int head_padded[3]; float scale[3]; int d, dp; };
+int launch_pack_mapped(const PackSrc& src, const PackMap& map, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
+                       int k_chunks, cudaStream_t st);
 
 // ---- persistent token GEMM (tc_gemm.cu) ---------------------------------------------------------------
 enum { AM_F32 = 0, AM_F32_LN = 1, AM_TILED = 2, AM_MERGE = 3 };
-enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_TILED = 2 };
+enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_TILED = 2, OUT_QKVH = 3 };
+
+// OUT_QKVH: per-(window, head) fp16 operand blobs for the HMMA attention core (attn_frag.cu).  GEMM
+// rows are in window order; the N axis is [q heads | k heads | v] with every q/k head padded to
+// `dp` columns (zero weight rows), v natural.  Destination arrays (w = window, h = head, t = token):
+//   Q [w][h][49][dp]   K [w][h][49][dp]   VT [w][h][d][QKVH_VT_STRIDE]  (V transposed, keys contiguous)
+static constexpr int QKVH_VT_STRIDE = 52;   // 49 keys + 3 zeros: 8-byte aligned rows, pairs/quads never read garbage
+struct QkvHeads {
+    __half* Q; __half* K; __half* VT;
+    int nh, d, dp;
+};
+static inline int qkvh_dp(int d) { return d <= 4 ? 4 : (d + 7) / 8 * 8; }
 
 struct TcGemm {
     // ---- caller fills ----
@@ -54,6 +71,9 @@ struct TcGemm {
     void* out; long long ldo; int out_col0; int N;
     int out_nkc;              // OUT_TILED: k-chunks per tile of the destination (= pad16(total columns)/8)
     int Hf, Wf, Cin, mh, mw;  // AM_MERGE: fine map (B,Hf,Wf,Cin) and merging factors
+    int win_order;            // GEMM rows are in window order: fp32 A producers gather source rows, OUT_F32 scatters rows
+    WinOrder wo;
+    QkvHeads qh;              // OUT_QKVH destination
     // ---- tc_gemm_plan fills ----
     int Kpad, KS, n_slabs, a_nkc, NA, NS, n_groups, chunks_per_group;
 };
@@ -62,7 +82,9 @@ int tc_gemm_pick_ks(int Kpad);          // k-slab width: largest of {64,48,32,16
 int tc_gemm_plan(TcGemm* p);          // needs K, a_mode, NCH, n_chunks, M
 int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st);
 // fp32 rows -> LayerNorm -> bf16 UMMA-tiled (pre-pass for wide rows, see tc_gemm.cu)
-int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st);
+// `wo` != null: output row m is the token win_order_token(*wo, m) of `in` (window order)
+int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st,
+                       const WinOrder* wo = nullptr);
 static constexpr int TC_LN_PREPASS_MIN_C = 96;   // rows at least this wide are normalised by the pre-pass
 
 // ---- fused small-channel MLP (tc_mlp.cu) -------------------------------------------------------------
@@ -84,11 +106,10 @@ int launch_tc_mlp(const TcMlp& t, cudaStream_t st);
 int launch_attn_core_bf16(const bf16* qkv, int qkv_fp16, long long ld, int koff, int voff, bf16* O, long long ldo, int o_nkc,
                           const float* table, const WinGeom& g, int nh, int d, cudaStream_t st);
 
-// tensor-core (HMMA) attention core for 7x7 windows, fp16 q/k/v, UMMA-tiled bf16 O (attn_mma.cu);
-// returns SF_ERR_UNSUPPORTED for shapes it does not cover (attn_mma_supported tells in advance);
-// qkv_nkc > 0: q/k/v are stored UMMA-tiled with that many 8-column chunks per 128-token tile
-bool attn_mma_supported(const WinGeom& g, int d);
-int launch_attn_core_mma(const bf16* qkv_fp16, long long ld, int qkv_nkc, int koff, int voff, bf16* O, int o_nkc, const float* table,
-                         const WinGeom& g, int nh, int d, cudaStream_t st);
+// HMMA attention core for 7x7 windows on the OUT_QKVH blobs (attn_frag.cu): every warp task loads its
+// m16n8k16 fragments straight from global memory, softmax on the accumulator fragments; O is written
+// bf16 UMMA-tiled in window order (o_nkc k-chunks per 128-row tile) for the projection GEMM.
+bool attn_frag_supported(const WinGeom& g, int nh, int d);
+int launch_attn_frag(const QkvHeads& qh, bf16* O, int o_nkc, const float* table, const WinGeom& g, cudaStream_t st);
 
 }  // namespace sf

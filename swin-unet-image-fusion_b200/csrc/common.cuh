@@ -112,6 +112,59 @@ __device__ __forceinline__ long long win_token_src(const WinGeom& g, int win, in
     return ((long long)b * g.Hp + sr) * g.Wp + sc;
 }
 
+// ---- division by a run-time constant (n < 2^31): q = umulhi(n, mul) >> shr ------------------
+struct FastDiv {
+    uint32_t mul, shr, d;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) lg++;
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+    return f;
+}
+__host__ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+#ifdef __CUDA_ARCH__
+    return f.d <= 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+#else
+    return f.d <= 1 ? n : (uint32_t)(((uint64_t)n * f.mul) >> 32) >> f.shr;
+#endif
+}
+
+// "window order" of the tokens of a (B,Hp,Wp) map: row m = window * T + t with the windows and
+// tokens numbered as in win_token_src.  The window-attention GEMMs of the bf16 path run on rows in
+// this order (gathered by the A producers, scattered back by the projection epilogue), so that a
+// window's q/k/v are contiguous for the attention core.
+struct WinOrder {
+    WinGeom g;
+    FastDiv dT, dnW, dnWw, dwsw;
+};
+static inline WinOrder make_winorder(const WinGeom& g) {
+    WinOrder o;
+    o.g = g;
+    o.dT = make_fastdiv((uint32_t)g.T);
+    o.dnW = make_fastdiv((uint32_t)(g.nWh * g.nWw));
+    o.dnWw = make_fastdiv((uint32_t)g.nWw);
+    o.dwsw = make_fastdiv((uint32_t)g.wsw);
+    return o;
+}
+// row m (window order) -> flat token index in the un-shifted map; *win / *tok receive (window, token in window)
+__device__ __forceinline__ long long win_order_token(const WinOrder& o, uint32_t m, uint32_t* win = nullptr, uint32_t* tok = nullptr) {
+    const WinGeom& g = o.g;
+    const uint32_t w = fdiv(m, o.dT), t = m - w * (uint32_t)g.T;
+    if (win) *win = w;
+    if (tok) *tok = t;
+    const uint32_t b = fdiv(w, o.dnW), wi = w - b * (uint32_t)(g.nWh * g.nWw);
+    const uint32_t wh = fdiv(wi, o.dnWw), ww = wi - wh * (uint32_t)g.nWw;
+    const uint32_t ti = fdiv(t, o.dwsw), tj = t - ti * (uint32_t)g.wsw;
+    const int sr = shift_src((int)(wh * g.wsh + ti), g.Hp, g.sh), sc = shift_src((int)(ww * g.wsw + tj), g.Wp, g.sw);
+    return ((long long)b * g.Hp + sr) * g.Wp + sc;
+}
+
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
 }  // namespace sf

@@ -89,6 +89,71 @@ int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float
     return SF_OK;
 }
 
+__global__ void k_pack_w_mapped(PackSrc src, PackMap map, int K, bf16* __restrict__ out, float* __restrict__ bias_out,
+                                int NR, int KR, int n_chunks, int k_chunks) {
+    const long long cpi = (long long)NR * KR / 8;
+    const long long total = cpi * n_chunks * k_chunks;
+    // packed row n -> (source, source row) or nothing
+    auto locate = [&](int n, int* s_out) -> int {
+        int start = 0;
+        for (int s = 0; s < map.nsrc; s++) {
+            if (n < start + map.rows[s]) {
+                int np = n - start;
+                *s_out = s;
+                if (!map.head_padded[s]) return np;
+                int h = np / map.dp, dd = np - h * map.dp;
+                return dd < map.d ? h * map.d + dd : -1;
+            }
+            start += map.rows[s];
+        }
+        *s_out = 0;
+        return -1;
+    };
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        long long img = c / cpi;
+        int ci = (int)(c - img * cpi);
+        int jk = (int)(img % k_chunks), jn = (int)(img / k_chunks);
+        int kc = ci / NR, r = ci - kc * NR;
+        int sidx;
+        const int srow = locate(jn * NR + r, &sidx);
+        uint32_t pk[4] = {0, 0, 0, 0};
+        if (srow >= 0) {
+            const float* row = src.w[sidx] + (long long)srow * K;
+            const float sc = map.scale[sidx];
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                int k = jk * KR + kc * 8 + e;
+                v[e] = k < K ? row[k] * sc : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+        }
+        *reinterpret_cast<uint4*>(out + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (bias_out) {
+        for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_chunks * NR; n += gridDim.x * blockDim.x) {
+            int sidx;
+            const int srow = locate(n, &sidx);
+            bias_out[n] = (srow >= 0 && src.b[sidx]) ? src.b[sidx][srow] * map.scale[sidx] : 0.f;
+        }
+    }
+}
+
+int launch_pack_mapped(const PackSrc& src, const PackMap& map, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
+                       int k_chunks, cudaStream_t st) {
+    long long total = (long long)NR * KR / 8 * n_chunks * k_chunks;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    double rows = 0;
+    for (int s = 0; s < map.nsrc; s++) rows += map.rows[s];
+    ProfScope ps("pack_weights_bf16", 0.0, 6.0 * rows * K, st);
+    k_pack_w_mapped<<<blocks, 256, 0, st>>>(src, map, K, out, bias_out, NR, KR, n_chunks, k_chunks);
+    SF_CHECK_LAUNCH("pack_weights_bf16");
+    return SF_OK;
+}
+
 // =============================================================================================
 // A producers (RESIDENT flavour): a [128 x Kpad] bf16 operand in the UMMA layout, LBO = 2064
 // =============================================================================================
@@ -101,7 +166,7 @@ static constexpr uint32_t LBO_T = lbo_dense(128);   // bulk-copied (tiled) A: 20
 template <bool LN, int NPER, int RB>
 __device__ __forceinline__ void produce_rows(uint8_t* sA, const float* __restrict__ A, long long lda, long long M, long long m0,
                                              int K, int Kpad, const float* __restrict__ g, const float* __restrict__ b, float eps,
-                                             int ptid) {
+                                             int ptid, const WinOrder* wo) {
     const int lane = ptid & 31, warp = ptid >> 5;
     const int nf4 = K >> 2, nslots = Kpad >> 2;
     int LPR = 1;
@@ -115,10 +180,11 @@ __device__ __forceinline__ void produce_rows(uint8_t* sA, const float* __restric
         for (int u = 0; u < RB; u++) {
             const long long m = m0 + warp * 32 + (it0 + u) * RPW + gr;
             const bool rowok = (it0 + u) < iters && m < M;
+            const long long ms = (wo && rowok) ? win_order_token(*wo, (uint32_t)m) : m;   // window order: gather the source row
 #pragma unroll
             for (int i = 0; i < NPER; i++) {
                 int q = gl + i * LPR;
-                v[u][i] = (rowok && q < nf4) ? *reinterpret_cast<const float4*>(A + m * lda + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][i] = (rowok && q < nf4) ? *reinterpret_cast<const float4*>(A + ms * lda + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
@@ -176,13 +242,14 @@ __device__ __forceinline__ void produce_rows(uint8_t* sA, const float* __restric
 template <bool LN, int NF4MAX>
 __device__ __forceinline__ void produce_rows_thread(uint8_t* sA, const float* __restrict__ A, long long lda, long long M,
                                                     long long m0, int K, int Kpad, const float* __restrict__ g,
-                                                    const float* __restrict__ b, float eps, int ptid) {
+                                                    const float* __restrict__ b, float eps, int ptid, const WinOrder* wo) {
     const int r = ptid;
     const long long m = m0 + r;
     const int nf4 = K >> 2, nkc = Kpad >> 3;
     const bool rowok = m < M;
     float4 v[NF4MAX];
-    const float4* src = reinterpret_cast<const float4*>(A + m * lda);
+    const long long ms = (wo && rowok) ? win_order_token(*wo, (uint32_t)m) : m;   // window order: gather the source row
+    const float4* src = reinterpret_cast<const float4*>(A + ms * lda);
 #pragma unroll
     for (int i = 0; i < NF4MAX; i++) v[i] = (rowok && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (LN) {
@@ -229,11 +296,12 @@ template <bool LN>
 __device__ __forceinline__ void produce_a_f32(uint8_t* sA, const TcGemm& p, long long m0, int ptid) {
     const float* A = reinterpret_cast<const float*>(p.A);
     const int nslots = p.Kpad >> 2;
-    if (nslots <= 8) produce_rows_thread<LN, 8>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
-    else if (nslots <= 16) produce_rows_thread<LN, 16>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
-    else if (nslots <= 32) produce_rows<LN, 1, 8>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
-    else if (nslots <= 64) produce_rows<LN, 2, 4>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
-    else produce_rows<LN, 3, 4>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
+    const WinOrder* wo = p.win_order ? &p.wo : nullptr;
+    if (nslots <= 8) produce_rows_thread<LN, 8>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid, wo);
+    else if (nslots <= 16) produce_rows_thread<LN, 16>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid, wo);
+    else if (nslots <= 32) produce_rows<LN, 1, 8>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid, wo);
+    else if (nslots <= 64) produce_rows<LN, 2, 4>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid, wo);
+    else produce_rows<LN, 3, 4>(sA, A, p.lda, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid, wo);
 }
 
 // patch-merge gather (a011:87-93): row (b,Y,X), k = (ph*mw+pw)*Cin + c <- in[b][Y*mh+ph][X*mw+pw][c]
@@ -274,17 +342,18 @@ __device__ __forceinline__ void produce_a_merge(uint8_t* sA, const TcGemm& p, lo
 // critical path and no per-n-group recomputation of the LayerNorm).  One warp per row.
 // =============================================================================================
 __global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
-                              bf16* __restrict__ out, long long M, int C, int Kpad, float eps) {
+                              bf16* __restrict__ out, long long M, int C, int Kpad, float eps, int gather, WinOrder wo) {
     const int lane = threadIdx.x & 31;
     const int nf4 = C >> 2, nslots = Kpad >> 2, nkc = Kpad >> 3;
     long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
     for (; row < M; row += stride) {
         float4 v[3];
+        const long long srow = gather ? win_order_token(wo, (uint32_t)row) : row;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             int q = lane + 32 * i;
-            v[i] = q < nf4 ? *reinterpret_cast<const float4*>(in + row * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = q < nf4 ? *reinterpret_cast<const float4*>(in + srow * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float s = 0.f;
 #pragma unroll
@@ -321,14 +390,16 @@ __global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restr
     }
 }
 
-int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st) {
+int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st,
+                       const WinOrder* wo) {
     const int Kpad = (int)pad16((uint32_t)C);
     SF_CHECK_ARG(C % 4 == 0 && Kpad <= TC_MAX_KPAD, "ln_to_tiled: unsupported row width %d", C);
     long long blocks = (M * 32 + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     if (blocks < 1) blocks = 1;
     ProfScope ps(prof_name("ln_to_tiled_c%d", C), 8.0 * (double)M * C, 6.0 * (double)M * C, st);
-    k_ln_to_tiled<<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps);
+    SF_CHECK_ARG(!wo || M < 2147483647LL, "ln_to_tiled: %lld rows exceed the window-order index range", M);
+    k_ln_to_tiled<<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
     SF_CHECK_LAUNCH("ln_to_tiled");
     return SF_OK;
 }
@@ -480,6 +551,10 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
             const long long tile = item / p.n_groups;
             const int group = (int)(item % p.n_groups);
             const long long m = tile * 128 + row;
+            // window-order rows: destination token of this row (projection scatter) / its (window, token) (q|k|v blobs)
+            long long mo = m;
+            uint32_t wwin = 0, wtok = 0;
+            if (((OUTMODE == OUT_F32 && p.win_order) || OUTMODE == OUT_QKVH) && m < p.M) mo = win_order_token(p.wo, (uint32_t)m, &wwin, &wtok);
             const int c0 = group * p.chunks_per_group;
             const int c1 = min(c0 + p.chunks_per_group, p.n_chunks);
             for (int c = c0; c < c1; c++, tcount++) {
@@ -533,9 +608,47 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
 #pragma unroll
                                 for (int i = 0; i < 16; i++) if (n0 + i < p.N) o16[i] = h[i];
                             }
+                        } else if (OUTMODE == OUT_QKVH) {
+                            const QkvHeads& qh = p.qh;
+                            const int hw = qh.nh * qh.dp;   // columns of the q (or k) block
+                            const int cg0 = p.out_col0 + n0;
+                            if (cg0 < 2 * hw) {
+                                __half* base = cg0 < hw ? qh.Q : qh.K;
+                                const int rem = cg0 < hw ? cg0 : cg0 - hw;
+                                if (qh.dp == 4) {
+#pragma unroll
+                                    for (int s4 = 0; s4 < 4; s4++) {
+                                        const int h = (rem >> 2) + s4;
+                                        *reinterpret_cast<uint2*>(base + (((size_t)wwin * qh.nh + h) * 49 + wtok) * 4) =
+                                            make_uint2(pack_f16x2(v[4 * s4], v[4 * s4 + 1]), pack_f16x2(v[4 * s4 + 2], v[4 * s4 + 3]));
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int s8 = 0; s8 < 2; s8++) {
+                                        const int cc = rem + 8 * s8, h = cc / qh.dp, dd = cc - h * qh.dp;
+                                        *reinterpret_cast<uint4*>(base + (((size_t)wwin * qh.nh + h) * 49 + wtok) * qh.dp + dd) =
+                                            make_uint4(pack_f16x2(v[8 * s8], v[8 * s8 + 1]), pack_f16x2(v[8 * s8 + 2], v[8 * s8 + 3]),
+                                                       pack_f16x2(v[8 * s8 + 4], v[8 * s8 + 5]), pack_f16x2(v[8 * s8 + 6], v[8 * s8 + 7]));
+                                    }
+                                }
+                            } else {
+                                // v: transposed, keys contiguous; the thread of the last token also writes the zero tail
+                                const int inner = qh.nh * qh.d;
+                                int ci = cg0 - 2 * hw, h = ci / qh.d, dd = ci - h * qh.d;
+#pragma unroll
+                                for (int i = 0; i < 16; i++, ci++) {
+                                    if (ci < inner) {
+                                        __half* dst = qh.VT + (((size_t)wwin * qh.nh + h) * qh.d + dd) * QKVH_VT_STRIDE + wtok;
+                                        const __half hv = __float2half_rn(v[i]);
+                                        if (wtok == 48) *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)__half_as_ushort(hv), 0u);
+                                        else *dst = hv;
+                                    }
+                                    if (++dd == qh.d) { dd = 0; h++; }
+                                }
+                            }
                         } else {
-                            float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + p.out_col0 + n0;
-                            const float* rs = p.residual ? p.residual + m * p.ldr + n0 : nullptr;
+                            float* o = reinterpret_cast<float*>(p.out) + mo * p.ldo + p.out_col0 + n0;
+                            const float* rs = p.residual ? p.residual + mo * p.ldr + n0 : nullptr;
                             const bool vec = ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
 #pragma unroll
                             for (int i = 0; i < 16; i += 4) {
@@ -596,6 +709,7 @@ int tc_gemm_plan(TcGemm* p) {
     } else {
         p->a_nkc = p->Kpad >> 3;
     }
+    SF_CHECK_ARG(!(p->win_order || p->out_mode == OUT_QKVH) || p->M < 2147483647LL, "tc_gemm: %lld rows exceed the window-order index range", p->M);
     const long long m_tiles = (p->M + 127) / 128;
     // spread the n-chunks of one m-tile over several CTAs only when there are too few m-tiles
     int groups = 1;
@@ -655,6 +769,9 @@ int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st) {
     if (p.a_mode == AM_TILED && p.out_mode == OUT_TILED) return launch_t<AM_TILED, OUT_TILED>(p, name, st);
     if (p.a_mode == AM_F32 && p.out_mode == OUT_F32) return launch_t<AM_F32, OUT_F32>(p, name, st);
     if (p.a_mode == AM_MERGE && p.out_mode == OUT_F32) return launch_t<AM_MERGE, OUT_F32>(p, name, st);
+    if (p.a_mode == AM_F32_LN && p.out_mode == OUT_QKVH) return launch_t<AM_F32_LN, OUT_QKVH>(p, name, st);
+    if (p.a_mode == AM_F32 && p.out_mode == OUT_QKVH) return launch_t<AM_F32, OUT_QKVH>(p, name, st);
+    if (p.a_mode == AM_TILED && p.out_mode == OUT_QKVH) return launch_t<AM_TILED, OUT_QKVH>(p, name, st);
     set_error("tc_gemm: unsupported mode combination (%d -> %d)", p.a_mode, p.out_mode);
     return SF_ERR_INVALID;
 }
