@@ -1,0 +1,314 @@
+// Attention core for 7x7 windows on tensor cores (a001:317-354), fp16 q/k/v rows -> bf16 O.
+//
+// Per (window, head): S = Q K^T and O = P V are 49x49xd / 49xdx49 products -- far too small for a
+// 128-row tcgen05 tile (one UMMA would be >60% padding and the accumulator would have to round-trip
+// through TMEM for the softmax), so they run as warp-level m16n8k16 HMMA tiles whose accumulator
+// fragments stay in registers, where the softmax is applied directly (FlashAttention-2 style).
+//
+// There is no shared memory and no block-level synchronisation in this kernel.  The q/k/v projection
+// GEMM (tc_gemm.cu) runs on rows in WINDOW ORDER (row = window*49 + token; its A producers apply the
+// cyclic shift and the window partition as index math) and writes fp16 rows
+//     [ q heads | k heads | v heads ],  every head padded to dp columns,  q pre-multiplied by d^-1/2 log2 e
+// so a window is 49 consecutive rows and every operand fragment is a direct global load (L1-resident:
+// one CTA works through all heads and row slabs of a window before moving on):
+//
+//   CTA  = one window at a time (persistent);  warp = (slab of 16 query rows, head parity)
+//   warp task = (window, head, slab)
+//       S[16 x 56] = Q_slab K^T        7 n-tiles x KSTEPS HMMAs, accumulators start at bias * log2 e
+//                                      (the slab's bias fragment lives in registers for the whole kernel:
+//                                       one 13x13 table shared by all heads and windows, a001:113-144)
+//       shift mask                     boundary windows only: two 28-bit key patterns per lane (a001:222-315)
+//       row max / row sum              2 quad shuffles each;  p = ex2(s - max)
+//       O[16 x dp] = P V               P (fp16) re-used in place as the A fragments; V fragments are loaded
+//                                      row-major and transposed in registers (movmatrix)
+//
+// Dot products do not care in which order k is summed, so the k index of the S MMAs is permuted to
+// make the loads wide: lane (gq, tq) feeds k-slots {2tq, 2tq+1} and {2tq+8, 2tq+9} from the 4
+// consecutive head dims 4tq..4tq+3 of a row (one LDG.64 for both registers, A and B alike).
+// O is written bf16 in the UMMA-tiled layout, window order, same head padding (the padded dims are
+// exact zeros: they come from zero V columns), which is the A operand the projection GEMM bulk-copies.
+#include <cuda_fp16.h>
+#include "bf16_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace sf {
+
+static constexpr int FT = 49;          // tokens per window
+static constexpr int AF_THREADS = 256; // 8 warps: slab = warp % 4, head parity = warp / 4
+
+struct AttnFragArgs {
+    const __half* qkv; int ld;        // fp16 rows, ld = 3 * hw
+    bf16* O; int o_nkc;               // hw / 8 k-chunks per 128-row tile
+    const float* table;
+    int nh, d, hw;                    // hw = nh * dp
+    int nWh, nWw, shift;
+    int nwin;
+    FastDiv dnW, dnWw;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcpf(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+    float y;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+    return y;
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// 8x8 b16 transpose across the warp: in: lane (gq, tq) holds M[gq][2tq..2tq+1]; out: M[2tq..2tq+1][gq]
+__device__ __forceinline__ uint32_t movm_trans(uint32_t x) {
+    uint32_t y;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint2 ldg64(const __half* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ uint32_t ldg32(const __half* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+
+// operand fragments of one (window, head) for one slab, as loaded (V still row-major)
+template <int KSTEPS, int NDT>
+struct Frags {
+    uint2 q[KSTEPS][2];     // rows r0 / r1: .x -> k-slots {2tq,2tq+1}, .y -> {2tq+8,2tq+9}
+    uint2 k[KSTEPS][7];     // n-tile nt: key nt*8 + gq
+    uint32_t v[NDT][7];     // d-tile dt, key tile kt: V[key kt*8 + gq][dims dt*8 + 2tq, +1]
+};
+
+// Per-lane pointers into the window-0 / head-0 rows (q row r0, k row gq, v row gq, lane column offsets
+// folded in); every other operand address is one of these plus a warp-uniform (window, head) offset
+// plus a compile-time immediate -- the row pitch LD is a template constant.
+struct LanePtrs {
+    const __half* q; const __half* k; const __half* v;
+    bool r0ok, r1ok, g0;       // rows r0 / r1 < 49; gq == 0 (the only lane group with a real key in key tile 6)
+};
+
+template <int KSTEPS, int NDT, bool DP4, int LD>
+__device__ __forceinline__ void load_frags(Frags<KSTEPS, NDT>& f, const LanePtrs& lp, size_t uoff, int tq) {
+    constexpr int dp = DP4 ? 4 : 8 * NDT;
+    const uint2 z = make_uint2(0u, 0u);
+    const __half* q = lp.q + uoff;
+    const __half* k = lp.k + uoff;
+    const __half* v = lp.v + uoff;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ks++) {
+        const bool cok = ks * 16 + 4 * tq < dp;
+        f.q[ks][0] = (cok && lp.r0ok) ? ldg64(q + ks * 16) : z;
+        f.q[ks][1] = (cok && lp.r1ok) ? ldg64(q + 8 * LD + ks * 16) : z;
+#pragma unroll
+        for (int nt = 0; nt < 7; nt++) f.k[ks][nt] = (cok && (nt < 6 || lp.g0)) ? ldg64(k + nt * 8 * LD + ks * 16) : z;
+    }
+#pragma unroll
+    for (int dt = 0; dt < NDT; dt++) {
+        const bool cok = dt * 8 + 2 * tq < dp;
+#pragma unroll
+        for (int kt = 0; kt < 7; kt++) f.v[dt][kt] = (cok && (kt < 6 || lp.g0)) ? ldg32(v + kt * 8 * LD + dt * 8) : 0u;
+    }
+}
+
+template <int KSTEPS, int NDT, bool DP4, int NH, bool PREFETCH, bool ONES>
+__global__ void __launch_bounds__(AF_THREADS, PREFETCH ? 2 : 1) k_attn_frag(AttnFragArgs a) {
+    constexpr int dp = DP4 ? 4 : 8 * NDT;
+    constexpr int HW = NH * dp, LD = 3 * HW, ONKC = HW / 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;   // fragment coordinates: row group / column pair
+    const int slab = warp & 3, sub = warp >> 2;
+    const int r0 = slab * 16 + gq, r1 = r0 + 8;
+    constexpr float LOG2E = 1.4426950408889634f;
+    constexpr float NEG = -1e30f;
+    constexpr float MASKED = -1.4426950e10f;   // the reference overwrites masked scores with -1e10 (a001:310), log2 domain
+    // d < dp: the projection GEMM put 1.0 into v's first padding column (bias 1, zero weights), so column d of
+    // P V is the row sum of the fp16 probabilities -- no separate summation
+    constexpr bool ones_col = ONES;
+
+    // ---- once per warp: bias fragment of this slab (x log2e; padded keys = -inf) and the key patterns of the shift mask
+    float bias[7][4];
+    uint32_t kh = 0, kw = 0;   // bit 2nt+e: key nt*8 + 2tq + e lies in the upper part (>= 4) of the window along H / W
+#pragma unroll
+    for (int nt = 0; nt < 7; nt++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int key = nt * 8 + 2 * tq + e;
+            float b0 = NEG, b1 = NEG;
+            if (key < FT) {
+                const int kr = key / 7, kc = key - kr * 7;
+                b0 = r0 < FT ? LOG2E * __ldg(a.table + (kr - r0 / 7 + 6) * 13 + (kc - r0 % 7 + 6)) : 0.f;
+                b1 = r1 < FT ? LOG2E * __ldg(a.table + (kr - r1 / 7 + 6) * 13 + (kc - r1 % 7 + 6)) : 0.f;
+                if (kr >= 4) kh |= 1u << (2 * nt + e);
+                if (kc >= 4) kw |= 1u << (2 * nt + e);
+            }
+            bias[nt][e] = b0;
+            bias[nt][2 + e] = b1;
+        }
+    }
+    // masked-slot patterns of this lane's two rows for a window in the last window row / column (a001:222-272:
+    // tokens 0..3 and 4..6 of such a window lie in different regions along that axis)
+    const uint32_t mh0 = (r0 < FT && r0 / 7 >= 4) ? ~kh : kh, mw0 = (r0 < FT && r0 % 7 >= 4) ? ~kw : kw;
+    const uint32_t mh1 = (r1 < FT && r1 / 7 >= 4) ? ~kh : kh, mw1 = (r1 < FT && r1 % 7 >= 4) ? ~kw : kw;
+
+    LanePtrs lp;
+    lp.r0ok = r0 < FT; lp.r1ok = r1 < FT; lp.g0 = gq == 0;
+    lp.q = a.qkv + r0 * LD + 4 * tq;
+    lp.k = a.qkv + gq * LD + HW + 4 * tq;
+    lp.v = a.qkv + gq * LD + 2 * HW + 2 * tq;
+    const int lsrc = (lane & ~3) | ((a.d & 7) >> 1);   // quad lane that holds column d of the last d-tile (ones_col)
+
+    int win = blockIdx.x, head = sub;
+    if (head >= NH) return;
+    Frags<KSTEPS, NDT> cur;
+    if (win < a.nwin) load_frags<KSTEPS, NDT, DP4, LD>(cur, lp, (size_t)win * (FT * LD) + head * dp, tq);
+
+    while (win < a.nwin) {
+        int nwin_ = win, nhead = head + 2;
+        if (nhead >= NH) { nhead = sub; nwin_ = win + gridDim.x; }
+        Frags<KSTEPS, NDT> nxt;
+        if (PREFETCH && nwin_ < a.nwin) load_frags<KSTEPS, NDT, DP4, LD>(nxt, lp, (size_t)nwin_ * (FT * LD) + nhead * dp, tq);
+
+        uint32_t m0 = 0, m1 = 0;
+        if (a.shift) {   // boundary windows of the shifted frame are the only ones whose tokens span several regions
+            const uint32_t wi = (uint32_t)win - fdiv((uint32_t)win, a.dnW) * (uint32_t)(a.nWh * a.nWw);
+            const uint32_t wh = fdiv(wi, a.dnWw), ww = wi - wh * (uint32_t)a.nWw;
+            if (wh == (uint32_t)a.nWh - 1) { m0 |= mh0; m1 |= mh1; }
+            if (ww == (uint32_t)a.nWw - 1) { m0 |= mw0; m1 |= mw1; }
+        }
+
+        // ---- S = Q K^T + bias ------------------------------------------------------------------------------
+        float s[7][4];
+#pragma unroll
+        for (int nt = 0; nt < 7; nt++) { s[nt][0] = bias[nt][0]; s[nt][1] = bias[nt][1]; s[nt][2] = bias[nt][2]; s[nt][3] = bias[nt][3]; }
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ks++)
+#pragma unroll
+            for (int nt = 0; nt < 7; nt++)
+                mma16816(s[nt], cur.q[ks][0].x, cur.q[ks][1].x, cur.q[ks][0].y, cur.q[ks][1].y, cur.k[ks][nt].x, cur.k[ks][nt].y);
+        if (m0 | m1) {
+#pragma unroll
+            for (int nt = 0; nt < 7; nt++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    if ((m0 >> (2 * nt + e)) & 1u) s[nt][e] = MASKED;
+                    if ((m1 >> (2 * nt + e)) & 1u) s[nt][2 + e] = MASKED;
+                }
+            }
+        }
+        // ---- softmax on the fragments ------------------------------------------------------------------------
+        float x0 = fmaxf(s[0][0], s[0][1]), x1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+        for (int nt = 1; nt < 7; nt++) {
+            x0 = max3f(x0, s[nt][0], s[nt][1]);
+            x1 = max3f(x1, s[nt][2], s[nt][3]);
+        }
+        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+        float l0 = 0.f, l1 = 0.f;
+        uint32_t pf[7][2];   // P as fp16 pairs: [nt][0] = row r0, [nt][1] = row r1
+#pragma unroll
+        for (int nt = 0; nt < 7; nt++) {
+            // n-tile 6 holds keys 48..55: only key 48 (column 0, lanes tq == 0) is real; the padded ones give ex2(-1e30) = 0
+            const float p0 = ex2f(s[nt][0] - x0), p2 = ex2f(s[nt][2] - x1);
+            const float p1 = nt < 6 ? ex2f(s[nt][1] - x0) : 0.f, p3 = nt < 6 ? ex2f(s[nt][3] - x1) : 0.f;
+            if (!ones_col) { l0 += p0 + p1; l1 += p2 + p3; }
+            pf[nt][0] = pack_h2(p0, p1);
+            pf[nt][1] = pack_h2(p2, p3);
+        }
+        // ---- O = P V : the score fragments of n-tiles (2j, 2j+1) are the A fragment of key step j ------------------
+        float o[NDT][4];
+#pragma unroll
+        for (int dt = 0; dt < NDT; dt++) { o[dt][0] = 0.f; o[dt][1] = 0.f; o[dt][2] = 0.f; o[dt][3] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t a0 = pf[2 * j][0], a1 = pf[2 * j][1];
+            const uint32_t a2 = (2 * j + 1 < 7) ? pf[2 * j + 1][0] : 0u, a3 = (2 * j + 1 < 7) ? pf[2 * j + 1][1] : 0u;
+#pragma unroll
+            for (int dt = 0; dt < NDT; dt++) {
+                const uint32_t b0 = movm_trans(cur.v[dt][2 * j]);
+                const uint32_t b1 = (2 * j + 1 < 7) ? movm_trans(cur.v[dt][2 * j + 1]) : 0u;
+                mma16816(o[dt], a0, a1, a2, a3, b0, b1);
+            }
+        }
+        if (ones_col) {   // row sums = column d of P V: last d-tile, quad lane (d%8)/2, element d%2
+            const float c0 = (a.d & 1) ? o[NDT - 1][1] : o[NDT - 1][0], c1 = (a.d & 1) ? o[NDT - 1][3] : o[NDT - 1][2];
+            l0 = __shfl_sync(0xffffffffu, c0, lsrc);
+            l1 = __shfl_sync(0xffffffffu, c1, lsrc);
+        } else {
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        }
+        // ---- O rows -> global, UMMA-tiled in window order: row m = win*49 + r, column head*dp + dim ---------------------
+        // element (m, col) at ((m >> 7) * ONKC + (col >> 3)) * 1024 + (m & 127) * 8 + (col & 7)
+        const float i0 = rcpf(l0), i1 = rcpf(l1);
+        if (!DP4 || tq < 2) {
+            const uint32_t mrow0 = (uint32_t)win * FT + (uint32_t)r0;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                if (half ? lp.r1ok : lp.r0ok) {
+                    const uint32_t m = mrow0 + 8 * half;
+                    const float inv = half ? i1 : i0;
+#pragma unroll
+                    for (int dt = 0; dt < NDT; dt++) {
+                        const int col = head * dp + dt * 8 + 2 * tq;
+                        const uint32_t off = ((m >> 7) * ONKC + (uint32_t)(col >> 3)) * 1024u + (m & 127u) * 8u + (uint32_t)(col & 7);
+                        *reinterpret_cast<uint32_t*>(a.O + off) = tc::pack_bf16x2(o[dt][2 * half] * inv, o[dt][2 * half + 1] * inv);
+                    }
+                }
+            }
+        }
+        win = nwin_; head = nhead;
+        if (PREFETCH) cur = nxt;
+        else if (win < a.nwin) load_frags<KSTEPS, NDT, DP4, LD>(cur, lp, (size_t)win * (FT * LD) + head * dp, tq);
+    }
+}
+
+template <int KSTEPS, int NDT, bool DP4, bool PREFETCH>
+static int launch_attn_frag_t(const AttnFragArgs& a, cudaStream_t st) {
+    constexpr int dp = DP4 ? 4 : 8 * NDT;
+    long long grid = 148LL * (PREFETCH ? 2 : 1);
+    if (grid > a.nwin) grid = a.nwin;
+    const int inner = a.nh * a.d;
+    const double mtok = (double)a.nwin * FT;
+    // algorithmic work: QK^T + PV = 4*49*N*C FLOP; bytes = q,k,v fp16 in + O bf16 out
+    ProfScope ps(prof_name("attn_core_frag_c%d", inner), 4.0 * FT * mtok * inner, 8.0 * mtok * inner, st);
+    if (a.d < dp) k_attn_frag<KSTEPS, NDT, DP4, 8, PREFETCH, true><<<(unsigned)grid, AF_THREADS, 0, st>>>(a);
+    else k_attn_frag<KSTEPS, NDT, DP4, 8, PREFETCH, false><<<(unsigned)grid, AF_THREADS, 0, st>>>(a);
+    SF_CHECK_LAUNCH("attn_core_frag");
+    return SF_OK;
+}
+
+bool attn_frag_supported(const WinGeom& g, int nh, int d) {
+    return g.T == FT && g.wsh == 7 && g.wsw == 7 && d >= 1 && d <= 48 && nh == 8;   // the row pitch is a compile-time constant
+}
+
+int launch_attn_frag(const __half* qkv, int ld, bf16* O, const float* table, const WinGeom& g, int nh, int d, cudaStream_t st) {
+    if (!attn_frag_supported(g, nh, d)) { set_error("attention core: unsupported window / head shape"); return SF_ERR_UNSUPPORTED; }
+    AttnFragArgs a{};
+    const int dp = qkvh_dp(d);
+    a.qkv = qkv; a.ld = ld; a.O = O; a.hw = nh * dp; a.o_nkc = a.hw / 8; a.table = table;
+    a.nh = nh; a.d = d; a.nWh = g.nWh; a.nWw = g.nWw; a.shift = g.shift;
+    const long long nwin = (long long)g.B * g.nWh * g.nWw;
+    SF_CHECK_ARG(ld == 3 * a.hw, "attention core: q|k|v rows must be %d columns wide", 3 * a.hw);
+    SF_CHECK_ARG((nwin * FT + 127) / 128 * 128 * (long long)ld < 2147483647LL, "attention core: %lld windows exceed the index range", nwin);
+    a.nwin = (int)nwin;
+    a.dnW = make_fastdiv((uint32_t)(g.nWh * g.nWw));
+    a.dnWw = make_fastdiv((uint32_t)g.nWw);
+    if (d <= 4) return launch_attn_frag_t<1, 1, true, true>(a, st);
+    if (d <= 8) return launch_attn_frag_t<1, 1, false, true>(a, st);
+    if (d <= 16) return launch_attn_frag_t<1, 2, false, true>(a, st);
+    if (d <= 24) return launch_attn_frag_t<2, 3, false, false>(a, st);
+    if (d <= 32) return launch_attn_frag_t<2, 4, false, false>(a, st);
+    if (d <= 40) return launch_attn_frag_t<3, 5, false, false>(a, st);
+    return launch_attn_frag_t<3, 6, false, false>(a, st);
+}
+
+}  // namespace sf

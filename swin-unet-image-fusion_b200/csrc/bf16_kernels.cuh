@@ -35,23 +35,19 @@ int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float
 // Same images, but the N axis is a concatenation of sources with their own layout: source s has
 // rows[s] packed rows; head_padded[s] != 0 means packed row n' = h*dp + dd maps to source row h*d + dd
 // (zero when dd >= d); weights and bias of source s are multiplied by scale[s].
-struct PackMap { int nsrc; int rows[3]; int head_padded[3]; float scale[3]; int d, dp; };
+// kdp > 0: the K axis is head padded too (packed column k' = h*kdp + dd <- source column h*kd + dd).
+// ones_pad[s] != 0: the first padding row of every head of source s (dd == d, needs d < dp) gets zero weights
+// and bias 1 -- a column of ones in the GEMM output (the attention core reads its softmax row sums off it).
+struct PackMap { int nsrc; int rows[3]; int head_padded[3]; float scale[3]; int d, dp; int kd, kdp; int ones_pad[3]; };
 int launch_pack_mapped(const PackSrc& src, const PackMap& map, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
                        int k_chunks, cudaStream_t st);
 
 // ---- persistent token GEMM (tc_gemm.cu) ---------------------------------------------------------------
 enum { AM_F32 = 0, AM_F32_LN = 1, AM_TILED = 2, AM_MERGE = 3 };
-enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_TILED = 2, OUT_QKVH = 3 };
+enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_TILED = 2 };
 
-// OUT_QKVH: per-(window, head) fp16 operand blobs for the HMMA attention core (attn_frag.cu).  GEMM
-// rows are in window order; the N axis is [q heads | k heads | v] with every q/k head padded to
-// `dp` columns (zero weight rows), v natural.  Destination arrays (w = window, h = head, t = token):
-//   Q [w][h][49][dp]   K [w][h][49][dp]   VT [w][h][d][QKVH_VT_STRIDE]  (V transposed, keys contiguous)
-static constexpr int QKVH_VT_STRIDE = 52;   // 49 keys + 3 zeros: 8-byte aligned rows, pairs/quads never read garbage
-struct QkvHeads {
-    __half* Q; __half* K; __half* VT;
-    int nh, d, dp;
-};
+// head-padded column layout shared by the window-attention GEMMs and the HMMA attention core
+// (attn_frag.cu): a head of d dims occupies dp columns (zeros above d), dp = 4 or a multiple of 8
 static inline int qkvh_dp(int d) { return d <= 4 ? 4 : (d + 7) / 8 * 8; }
 
 struct TcGemm {
@@ -73,7 +69,6 @@ struct TcGemm {
     int Hf, Wf, Cin, mh, mw;  // AM_MERGE: fine map (B,Hf,Wf,Cin) and merging factors
     int win_order;            // GEMM rows are in window order: fp32 A producers gather source rows, OUT_F32 scatters rows
     WinOrder wo;
-    QkvHeads qh;              // OUT_QKVH destination
     // ---- tc_gemm_plan fills ----
     int Kpad, KS, n_slabs, a_nkc, NA, NS, n_groups, chunks_per_group;
 };
@@ -106,10 +101,10 @@ int launch_tc_mlp(const TcMlp& t, cudaStream_t st);
 int launch_attn_core_bf16(const bf16* qkv, int qkv_fp16, long long ld, int koff, int voff, bf16* O, long long ldo, int o_nkc,
                           const float* table, const WinGeom& g, int nh, int d, cudaStream_t st);
 
-// HMMA attention core for 7x7 windows on the OUT_QKVH blobs (attn_frag.cu): every warp task loads its
-// m16n8k16 fragments straight from global memory, softmax on the accumulator fragments; O is written
-// bf16 UMMA-tiled in window order (o_nkc k-chunks per 128-row tile) for the projection GEMM.
+// HMMA attention core for 7x7 windows (attn_frag.cu).  qkv: fp16 rows in window order (row = window*49 + token),
+// ld columns = [q heads | k heads | v heads], every head padded to dp = qkvh_dp(d) columns, q pre-scaled by
+// d^-1/2 * log2(e).  O: bf16, UMMA-tiled (nh*dp/8 k-chunks per 128-row tile), same row order and head padding.
 bool attn_frag_supported(const WinGeom& g, int nh, int d);
-int launch_attn_frag(const QkvHeads& qh, bf16* O, int o_nkc, const float* table, const WinGeom& g, cudaStream_t st);
+int launch_attn_frag(const __half* qkv, int ld, bf16* O, const float* table, const WinGeom& g, int nh, int d, cudaStream_t st);
 
 }  // namespace sf

@@ -1,7 +1,7 @@
 // SF_PREC_BF16 operator implementations: which tensor-core kernels run for each fused operator, how
 // the weights are packed (once, when the caller provides a `packed` buffer; per call otherwise) and
 // how the caller's workspace is carved.  Every linear layer goes through tcgen05.mma (tc_gemm.cu);
-// the per-window attention core runs on HMMA tiles (attn_mma.cu); LayerNorm, softmax, bias, ELU and
+// the per-window attention core runs on HMMA tiles (attn_frag.cu); LayerNorm, softmax, bias, ELU and
 // the residual stream stay fp32.
 #include "bf16_kernels.cuh"
 #include "fp32_kernels.cuh"
@@ -45,7 +45,9 @@ static void bind_packed(TcGemm& t, const PackedGemm& g, const char* packed_base)
 // =============================================================================================
 struct WaPlan {
     bool self_attn;
-    int inner;
+    bool frag;                    // 7x7 windows: window-order GEMMs + HMMA attention core (attn_frag.cu)
+    int inner, dp, hw;            // frag: padded head width of the q / k / v / O columns, hw = heads * dp
+    WinGeom geom;
     PackedGemm q, kv, o;          // q: stacked q|k|v for self attention
     size_t packed_bytes;
     bool prepass_q, prepass_kv;
@@ -57,14 +59,24 @@ static WaPlan wa_plan(const sf_window_attn_params* p) {
     const long long M = (long long)p->B * p->Hp * p->Wp;
     w.self_attn = p->kv_src == p->q_src && p->ln_q_gamma == p->ln_kv_gamma && p->ln_q_beta == p->ln_kv_beta;
     w.inner = p->num_heads * p->head_dim;
+    w.geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
+    w.frag = attn_frag_supported(w.geom, p->num_heads, p->head_dim) && M < 2147483647LL / 64;
+    w.dp = qkvh_dp(p->head_dim);
+    w.hw = p->num_heads * w.dp;
     Carver pc;
-    w.q = plan_packed(pc, w.self_attn ? 3 * w.inner : w.inner, p->C);
-    if (!w.self_attn) w.kv = plan_packed(pc, 2 * w.inner, p->C);
-    w.o = plan_packed(pc, p->C, w.inner);
+    if (w.frag) {
+        w.q = plan_packed(pc, w.self_attn ? 3 * w.hw : w.hw, p->C);
+        if (!w.self_attn) w.kv = plan_packed(pc, 2 * w.hw, p->C);
+    } else {
+        w.q = plan_packed(pc, w.self_attn ? 3 * w.inner : w.inner, p->C);
+        if (!w.self_attn) w.kv = plan_packed(pc, 2 * w.inner, p->C);
+    }
+    w.o = plan_packed(pc, p->C, w.frag ? w.hw : w.inner);
     w.packed_bytes = pc.off;
     Carver c;
-    w.off_qkv = c.take(tiled_elems(M, 3 * w.inner) * sizeof(bf16));   // rows or UMMA-tiled (padded), see fwd
-    w.off_o = c.take(tiled_elems(M, w.inner) * sizeof(bf16));
+    const int ocols = w.frag ? w.hw : w.inner;   // columns of q, k, v and O rows
+    w.off_qkv = c.take(tiled_elems(M, 3 * ocols) * sizeof(bf16));   // fp16 rows
+    w.off_o = c.take(tiled_elems(M, ocols) * sizeof(bf16));
     w.off_packed = c.take(p->packed ? 0 : w.packed_bytes);
     w.prepass_q = p->ln_q_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
     w.prepass_kv = !w.self_attn && p->ln_kv_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
@@ -93,7 +105,23 @@ int window_attn_pack_bf16(const sf_window_attn_params* p, void* packed, size_t b
     if (bytes < w.packed_bytes) { set_error("sf_window_attn_pack: buffer too small (%zu B given, %zu needed)", bytes, w.packed_bytes); return SF_ERR_WORKSPACE; }
     char* base = reinterpret_cast<char*>(packed);
     const int inner = w.inner, C = p->C;
-    if (w.self_attn) {
+    if (w.frag) {
+        // N axis = [q heads | k heads | v heads], every head padded to dp columns; q (weights and bias) carries d^-1/2 * log2(e):
+        // the attention core works in the log2 domain (a001:32-34,335 applies the scale after the product -- same value)
+        const float qs = 1.4426950408889634f / sqrtf((float)p->head_dim);
+        if (w.self_attn) {
+            PackSrc s{{p->wq, p->wk, p->wv}, {p->bq, p->bk, p->bv}};
+            PackMap m{3, {w.hw, w.hw, w.hw}, {1, 1, 1}, {qs, 1.f, 1.f}, p->head_dim, w.dp, 0, 0, {0, 0, 1}};
+            SF_TRY(launch_pack_mapped(s, m, C, (bf16*)(base + w.q.off_w), (float*)(base + w.q.off_b), w.q.nch, w.q.ks, w.q.nc, w.q.nslabs, st));
+        } else {
+            PackSrc s1{{p->wq, nullptr, nullptr}, {p->bq, nullptr, nullptr}};
+            PackMap m1{1, {w.hw, 0, 0}, {1, 0, 0}, {qs, 1.f, 1.f}, p->head_dim, w.dp, 0, 0, {0, 0, 0}};
+            SF_TRY(launch_pack_mapped(s1, m1, C, (bf16*)(base + w.q.off_w), (float*)(base + w.q.off_b), w.q.nch, w.q.ks, w.q.nc, w.q.nslabs, st));
+            PackSrc s2{{p->wk, p->wv, nullptr}, {p->bk, p->bv, nullptr}};
+            PackMap m2{2, {w.hw, w.hw, 0}, {1, 1, 0}, {1.f, 1.f, 1.f}, p->head_dim, w.dp, 0, 0, {0, 1, 0}};
+            SF_TRY(launch_pack_mapped(s2, m2, C, (bf16*)(base + w.kv.off_w), (float*)(base + w.kv.off_b), w.kv.nch, w.kv.ks, w.kv.nc, w.kv.nslabs, st));
+        }
+    } else if (w.self_attn) {
         PackSrc s{{p->wq, p->wk, p->wv}, {p->bq, p->bk, p->bv}};
         SF_TRY(launch_pack(s, 3, inner, C, (bf16*)(base + w.q.off_w), (float*)(base + w.q.off_b), w.q.nch, w.q.ks, w.q.nc, w.q.nslabs, st));
     } else {
@@ -103,7 +131,12 @@ int window_attn_pack_bf16(const sf_window_attn_params* p, void* packed, size_t b
         SF_TRY(launch_pack(s2, 2, inner, C, (bf16*)(base + w.kv.off_w), (float*)(base + w.kv.off_b), w.kv.nch, w.kv.ks, w.kv.nc, w.kv.nslabs, st));
     }
     PackSrc so{{p->wo, nullptr, nullptr}, {p->bo, nullptr, nullptr}};
-    SF_TRY(launch_pack(so, 1, C, inner, (bf16*)(base + w.o.off_w), (float*)(base + w.o.off_b), w.o.nch, w.o.ks, w.o.nc, w.o.nslabs, st));
+    if (w.frag) {   // the K axis of the projection follows O's head padding
+        PackMap mo{1, {C, 0, 0}, {0, 0, 0}, {1.f, 1.f, 1.f}, 0, 0, p->head_dim, w.dp, {0, 0, 0}};
+        SF_TRY(launch_pack_mapped(so, mo, inner, (bf16*)(base + w.o.off_w), (float*)(base + w.o.off_b), w.o.nch, w.o.ks, w.o.nc, w.o.nslabs, st));
+    } else {
+        SF_TRY(launch_pack(so, 1, C, inner, (bf16*)(base + w.o.off_w), (float*)(base + w.o.off_b), w.o.nch, w.o.ks, w.o.nc, w.o.nslabs, st));
+    }
     return SF_OK;
 }
 
@@ -121,21 +154,22 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
         SF_TRY(window_attn_pack_bf16(p, base + w.off_packed, w.packed_bytes, st));
         pk = base + w.off_packed;
     }
-    // projections -> q|k|v, fp16.  With the HMMA attention core they are written UMMA-tiled
-    // ([tile][chunk][row][8]: the epilogue's 16-byte stores are contiguous across a warp) and the
-    // core gathers 16-byte chunks from it; the CUDA-core fallback reads plain rows.
-    WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
-    const bool use_mma = attn_mma_supported(geom, p->head_dim) && inner % 8 == 0;
-    const int qkv_nkc = use_mma ? (int)pad16((uint32_t)(3 * inner)) / 8 : 0;
+    // projections -> q|k|v (fp16).  7x7 windows: the GEMMs run on rows in window order (A producers gather, shift and
+    // partition as index math) and write per-(window, head) blobs for the HMMA core; otherwise plain fp16 rows.
+    const WinGeom& geom = w.geom;
+    const WinOrder wo = make_winorder(geom);
+    const int ocols = w.frag ? w.hw : inner;   // columns of q, k, v (head padded when w.frag)
     TcGemm g{};
-    g.M = M; g.K = C; g.lda = C; g.eps = p->ln_eps; g.out_mode = use_mma ? OUT_TILED : OUT_BF16; g.out_fp16 = 1;
-    g.out = qkv; g.ldo = 3 * inner; g.out_nkc = qkv_nkc;
+    g.M = M; g.K = C; g.lda = C; g.eps = p->ln_eps; g.out_fp16 = 1;
+    g.out_mode = OUT_BF16; g.out = qkv; g.ldo = 3 * ocols;
+    g.N = w.self_attn ? 3 * ocols : ocols;
+    if (w.frag) { g.win_order = 1; g.wo = wo; }
     g.A = p->q_src; g.ln_g = p->ln_q_gamma; g.ln_b = p->ln_q_beta; g.a_mode = p->ln_q_gamma ? AM_F32_LN : AM_F32;
     bind_packed(g, w.q, pk);
-    g.out_col0 = 0; g.N = w.self_attn ? 3 * inner : inner;
+    g.out_col0 = 0;
     if (w.prepass_q) {   // wide rows: LayerNorm once into the UMMA-tiled layout, GEMM streams it
         bf16* nq = reinterpret_cast<bf16*>(base + w.off_nq);
-        SF_TRY(launch_ln_to_tiled(p->q_src, p->ln_q_gamma, p->ln_q_beta, nq, M, C, p->ln_eps, st));
+        SF_TRY(launch_ln_to_tiled(p->q_src, p->ln_q_gamma, p->ln_q_beta, nq, M, C, p->ln_eps, st, w.frag ? &wo : nullptr));
         g.A = nq; g.a_mode = AM_TILED;
     }
     SF_TRY(tc_gemm_plan(&g));
@@ -144,27 +178,29 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
         TcGemm k = g;
         k.A = p->kv_src; k.ln_g = p->ln_kv_gamma; k.ln_b = p->ln_kv_beta; k.a_mode = p->ln_kv_gamma ? AM_F32_LN : AM_F32;
         bind_packed(k, w.kv, pk);
-        k.out_col0 = inner; k.N = 2 * inner;
+        k.out_col0 = ocols; k.N = 2 * ocols;
         if (w.prepass_kv) {
             bf16* nkv = reinterpret_cast<bf16*>(base + w.off_nkv);
-            SF_TRY(launch_ln_to_tiled(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, nkv, M, C, p->ln_eps, st));
+            SF_TRY(launch_ln_to_tiled(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, nkv, M, C, p->ln_eps, st, w.frag ? &wo : nullptr));
             k.A = nkv; k.a_mode = AM_TILED;
         }
         SF_TRY(tc_gemm_plan(&k));
         SF_TRY(launch_tc_gemm(k, prof_name("tc_gemm_kv_c%d", C), st));
     }
-    // attention core -> O (bf16, UMMA-tiled so the projection GEMM can bulk-copy it)
-    const int o_nkc = (int)pad16((uint32_t)inner) / 8;
-    int arc;
-    if (use_mma) arc = launch_attn_core_mma(qkv, 3 * inner, qkv_nkc, inner, 2 * inner, O, o_nkc, p->bias_table, geom, p->num_heads, p->head_dim, st);
-    else arc = launch_attn_core_bf16(qkv, 1, 3 * inner, inner, 2 * inner, O, 0, o_nkc, p->bias_table, geom, p->num_heads, p->head_dim, st);
-    SF_TRY(arc);
-    // output projection (+ residual) -> out fp32 rows
+    // attention core -> O (bf16, UMMA-tiled so the projection GEMM can bulk-copy it; window order when w.frag)
+    if (w.frag) {
+        SF_TRY(launch_attn_frag(reinterpret_cast<const __half*>(qkv), 3 * ocols, O, p->bias_table, geom, p->num_heads, p->head_dim, st));
+    } else {
+        const int o_nkc = (int)pad16((uint32_t)inner) / 8;
+        SF_TRY(launch_attn_core_bf16(qkv, 1, 3 * inner, inner, 2 * inner, O, 0, o_nkc, p->bias_table, geom, p->num_heads, p->head_dim, st));
+    }
+    // output projection (+ residual) -> out fp32 rows (scattered back: window reverse and un-shift, a001:373-398,442-445)
     TcGemm o{};
-    o.M = M; o.K = inner; o.A = O; o.a_mode = AM_TILED; o.out_mode = OUT_F32;
+    o.M = M; o.K = ocols; o.A = O; o.a_mode = AM_TILED; o.out_mode = OUT_F32;
     bind_packed(o, w.o, pk);
     o.residual = p->residual; o.ldr = C;
     o.out = p->out; o.ldo = C; o.out_col0 = 0; o.N = C;
+    if (w.frag) { o.win_order = 1; o.wo = wo; }
     SF_TRY(tc_gemm_plan(&o));
     SF_TRY(launch_tc_gemm(o, prof_name("tc_gemm_proj_c%d", C), st));
     return SF_OK;

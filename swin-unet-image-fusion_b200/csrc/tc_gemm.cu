@@ -102,6 +102,7 @@ __global__ void k_pack_w_mapped(PackSrc src, PackMap map, int K, bf16* __restric
                 *s_out = s;
                 if (!map.head_padded[s]) return np;
                 int h = np / map.dp, dd = np - h * map.dp;
+                if (dd == map.d && map.ones_pad[s]) return -2;   // zero weights, bias 1: a column of ones
                 return dd < map.d ? h * map.d + dd : -1;
             }
             start += map.rows[s];
@@ -124,6 +125,10 @@ __global__ void k_pack_w_mapped(PackSrc src, PackMap map, int K, bf16* __restric
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 int k = jk * KR + kc * 8 + e;
+                if (map.kdp > 0) {   // head-padded K axis
+                    int h = k / map.kdp, dd = k - h * map.kdp;
+                    k = dd < map.kd ? h * map.kd + dd : K;
+                }
                 v[e] = k < K ? row[k] * sc : 0.f;
             }
 #pragma unroll
@@ -135,7 +140,7 @@ __global__ void k_pack_w_mapped(PackSrc src, PackMap map, int K, bf16* __restric
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_chunks * NR; n += gridDim.x * blockDim.x) {
             int sidx;
             const int srow = locate(n, &sidx);
-            bias_out[n] = (srow >= 0 && src.b[sidx]) ? src.b[sidx][srow] * map.scale[sidx] : 0.f;
+            bias_out[n] = srow == -2 ? 1.f : ((srow >= 0 && src.b[sidx]) ? src.b[sidx][srow] * map.scale[sidx] : 0.f);
         }
     }
 }
@@ -551,10 +556,9 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
             const long long tile = item / p.n_groups;
             const int group = (int)(item % p.n_groups);
             const long long m = tile * 128 + row;
-            // window-order rows: destination token of this row (projection scatter) / its (window, token) (q|k|v blobs)
+            // window-order rows: destination token of this row (projection scatter: window reverse + un-shift)
             long long mo = m;
-            uint32_t wwin = 0, wtok = 0;
-            if (((OUTMODE == OUT_F32 && p.win_order) || OUTMODE == OUT_QKVH) && m < p.M) mo = win_order_token(p.wo, (uint32_t)m, &wwin, &wtok);
+            if (OUTMODE == OUT_F32 && p.win_order && m < p.M) mo = win_order_token(p.wo, (uint32_t)m);
             const int c0 = group * p.chunks_per_group;
             const int c1 = min(c0 + p.chunks_per_group, p.n_chunks);
             for (int c = c0; c < c1; c++, tcount++) {
@@ -607,44 +611,6 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                                 uint16_t* o16 = reinterpret_cast<uint16_t*>(o);
 #pragma unroll
                                 for (int i = 0; i < 16; i++) if (n0 + i < p.N) o16[i] = h[i];
-                            }
-                        } else if (OUTMODE == OUT_QKVH) {
-                            const QkvHeads& qh = p.qh;
-                            const int hw = qh.nh * qh.dp;   // columns of the q (or k) block
-                            const int cg0 = p.out_col0 + n0;
-                            if (cg0 < 2 * hw) {
-                                __half* base = cg0 < hw ? qh.Q : qh.K;
-                                const int rem = cg0 < hw ? cg0 : cg0 - hw;
-                                if (qh.dp == 4) {
-#pragma unroll
-                                    for (int s4 = 0; s4 < 4; s4++) {
-                                        const int h = (rem >> 2) + s4;
-                                        *reinterpret_cast<uint2*>(base + (((size_t)wwin * qh.nh + h) * 49 + wtok) * 4) =
-                                            make_uint2(pack_f16x2(v[4 * s4], v[4 * s4 + 1]), pack_f16x2(v[4 * s4 + 2], v[4 * s4 + 3]));
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int s8 = 0; s8 < 2; s8++) {
-                                        const int cc = rem + 8 * s8, h = cc / qh.dp, dd = cc - h * qh.dp;
-                                        *reinterpret_cast<uint4*>(base + (((size_t)wwin * qh.nh + h) * 49 + wtok) * qh.dp + dd) =
-                                            make_uint4(pack_f16x2(v[8 * s8], v[8 * s8 + 1]), pack_f16x2(v[8 * s8 + 2], v[8 * s8 + 3]),
-                                                       pack_f16x2(v[8 * s8 + 4], v[8 * s8 + 5]), pack_f16x2(v[8 * s8 + 6], v[8 * s8 + 7]));
-                                    }
-                                }
-                            } else {
-                                // v: transposed, keys contiguous; the thread of the last token also writes the zero tail
-                                const int inner = qh.nh * qh.d;
-                                int ci = cg0 - 2 * hw, h = ci / qh.d, dd = ci - h * qh.d;
-#pragma unroll
-                                for (int i = 0; i < 16; i++, ci++) {
-                                    if (ci < inner) {
-                                        __half* dst = qh.VT + (((size_t)wwin * qh.nh + h) * qh.d + dd) * QKVH_VT_STRIDE + wtok;
-                                        const __half hv = __float2half_rn(v[i]);
-                                        if (wtok == 48) *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)__half_as_ushort(hv), 0u);
-                                        else *dst = hv;
-                                    }
-                                    if (++dd == qh.d) { dd = 0; h++; }
-                                }
                             }
                         } else {
                             float* o = reinterpret_cast<float*>(p.out) + mo * p.ldo + p.out_col0 + n0;
@@ -709,7 +675,7 @@ int tc_gemm_plan(TcGemm* p) {
     } else {
         p->a_nkc = p->Kpad >> 3;
     }
-    SF_CHECK_ARG(!(p->win_order || p->out_mode == OUT_QKVH) || p->M < 2147483647LL, "tc_gemm: %lld rows exceed the window-order index range", p->M);
+    SF_CHECK_ARG(!p->win_order || p->M < 2147483647LL, "tc_gemm: %lld rows exceed the window-order index range", p->M);
     const long long m_tiles = (p->M + 127) / 128;
     // spread the n-chunks of one m-tile over several CTAs only when there are too few m-tiles
     int groups = 1;
@@ -769,9 +735,6 @@ int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st) {
     if (p.a_mode == AM_TILED && p.out_mode == OUT_TILED) return launch_t<AM_TILED, OUT_TILED>(p, name, st);
     if (p.a_mode == AM_F32 && p.out_mode == OUT_F32) return launch_t<AM_F32, OUT_F32>(p, name, st);
     if (p.a_mode == AM_MERGE && p.out_mode == OUT_F32) return launch_t<AM_MERGE, OUT_F32>(p, name, st);
-    if (p.a_mode == AM_F32_LN && p.out_mode == OUT_QKVH) return launch_t<AM_F32_LN, OUT_QKVH>(p, name, st);
-    if (p.a_mode == AM_F32 && p.out_mode == OUT_QKVH) return launch_t<AM_F32, OUT_QKVH>(p, name, st);
-    if (p.a_mode == AM_TILED && p.out_mode == OUT_QKVH) return launch_t<AM_TILED, OUT_QKVH>(p, name, st);
     set_error("tc_gemm: unsupported mode combination (%d -> %d)", p.a_mode, p.out_mode);
     return SF_ERR_INVALID;
 }
