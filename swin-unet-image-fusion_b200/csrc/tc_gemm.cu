@@ -18,6 +18,7 @@
 // Pipelines: A buffers (full/empty), k-slab ring (full/empty), two TMEM accumulators (full/empty),
 // so the producers work on item i+1 and the epilogue on chunk j-1 while the tensor core runs chunk j.
 #include <algorithm>
+#include <type_traits>
 #include <initializer_list>
 #include "bf16_kernels.cuh"
 #include "tc_common.cuh"
@@ -243,20 +244,27 @@ __device__ __forceinline__ void produce_rows(uint8_t* sA, const float* __restric
 // of a warp are independent instruction streams, st.shared of 16-byte chunks is conflict-free
 // (consecutive lanes = consecutive rows = consecutive 16 bytes).  A warp reads 32 consecutive rows,
 // i.e. one contiguous 32*K*4-byte span; the sectors a single LDG.128 half-uses are completed by the
-// next one out of L1.
-template <bool LN, int NF4MAX>
-__device__ __forceinline__ void produce_rows_thread(uint8_t* sA, const float* __restrict__ A, long long lda, long long M,
-                                                    long long m0, int K, int Kpad, const float* __restrict__ g,
-                                                    const float* __restrict__ b, float eps, int ptid, const WinOrder* wo) {
-    const int r = ptid;
-    const long long m = m0 + r;
-    const int nf4 = K >> 2, nkc = Kpad >> 3;
+// next one out of L1.  Split into a load and a finish phase so that the producer loop can keep the
+// NEXT tile's rows in flight while it normalises the current one (these GEMMs are HBM-bound and a
+// producer group that waits out every load latency cannot cover it).
+template <int NF4MAX>
+__device__ __forceinline__ void load_row_thread(float4 (&v)[NF4MAX], const float* __restrict__ A, long long lda, long long M,
+                                                long long m0, int K, int ptid, const WinOrder* wo) {
+    const long long m = m0 + ptid;
+    const int nf4 = K >> 2;
     const bool rowok = m < M;
-    float4 v[NF4MAX];
     const long long ms = (wo && rowok) ? win_order_token(*wo, (uint32_t)m) : m;   // window order: gather the source row
     const float4* src = reinterpret_cast<const float4*>(A + ms * lda);
 #pragma unroll
     for (int i = 0; i < NF4MAX; i++) v[i] = (rowok && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <bool LN, int NF4MAX>
+__device__ __forceinline__ void finish_row_thread(uint8_t* sA, float4 (&v)[NF4MAX], long long M, long long m0, int K, int Kpad,
+                                                  const float* __restrict__ g, const float* __restrict__ b, float eps, int ptid) {
+    const int r = ptid;
+    const int nf4 = K >> 2, nkc = Kpad >> 3;
+    const bool rowok = m0 + r < M;
     if (LN) {
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -295,6 +303,15 @@ __device__ __forceinline__ void produce_rows_thread(uint8_t* sA, const float* __
             *reinterpret_cast<uint4*>(sA + (uint32_t)c * LBO_P + (uint32_t)r * 16) = pk;
         }
     }
+}
+
+template <bool LN, int NF4MAX>
+__device__ __forceinline__ void produce_rows_thread(uint8_t* sA, const float* __restrict__ A, long long lda, long long M,
+                                                    long long m0, int K, int Kpad, const float* __restrict__ g,
+                                                    const float* __restrict__ b, float eps, int ptid, const WinOrder* wo) {
+    float4 v[NF4MAX];
+    load_row_thread<NF4MAX>(v, A, lda, M, m0, K, ptid, wo);
+    finish_row_thread<LN, NF4MAX>(sA, v, M, m0, K, Kpad, g, b, eps, ptid);
 }
 
 template <bool LN>
@@ -413,7 +430,7 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
 // the kernel
 // =============================================================================================
 struct GemmSmem {
-    uint32_t a_bytes, a_off[2], w_off, stage_bytes, slabA_bytes, slabW_bytes, bar_off, total;
+    uint32_t a_bytes, a_off[2], w_off, stage_bytes, slabA_bytes, slabW_bytes, bias_off, bar_off, total;
 };
 
 __host__ __device__ static inline GemmSmem gemm_smem_layout(const TcGemm& p) {
@@ -426,7 +443,8 @@ __host__ __device__ static inline GemmSmem gemm_smem_layout(const TcGemm& p) {
     s.slabW_bytes = (uint32_t)p.NCH * (uint32_t)p.KS * 2u;
     s.slabA_bytes = stream ? (uint32_t)(p.KS >> 3) * LBO_T : 0u;
     s.stage_bytes = align128(s.slabW_bytes) + align128(s.slabA_bytes);
-    s.bar_off = s.w_off + (uint32_t)p.NS * s.stage_bytes;
+    s.bias_off = s.w_off + (uint32_t)p.NS * s.stage_bytes;
+    s.bar_off = s.bias_off + align128(p.bias ? (uint32_t)p.n_chunks * (uint32_t)p.NCH * 4u : 0u);
     s.total = s.bar_off + 256;
     return s;
 }
@@ -458,6 +476,12 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
         fence_mbar_init();
     }
     if (warp == PW + 1) tmem_alloc(tmem_slot, ncols);
+    // bias vector of all n-chunks -> shared memory (the epilogue reads it as broadcast float4s)
+    const float* sbias = reinterpret_cast<const float*>(smem + L.bias_off);
+    if (p.bias) {
+        float* sb = reinterpret_cast<float*>(smem + L.bias_off);
+        for (int i = tid; i < p.n_chunks * p.NCH; i += blockDim.x) sb[i] = __ldg(p.bias + i);
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -467,7 +491,33 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
         // ------------------------------ A producers -------------------------------------------------
         const uint32_t grp = (uint32_t)warp >> 2;
         const int ptid = tid & 127;
-        if (!STREAM && (NA == 2 || grp == 0)) {
+        const int nslots_a = p.Kpad >> 2;
+        if ((AMODE == AM_F32 || AMODE == AM_F32_LN) && nslots_a <= 8 && (NA == 2 || grp == 0)) {
+            // thread-per-row producers, software pipelined: the rows of this group's NEXT item are in flight
+            // (registers) while the current ones are normalised and written to shared memory
+            const float* Af = reinterpret_cast<const float*>(p.A);
+            const WinOrder* wo = p.win_order ? &p.wo : nullptr;
+            const long long step = (long long)gridDim.x * NA;
+            auto run = [&](auto nf4tag) {
+                constexpr int NF = decltype(nf4tag)::value;
+                float4 vn[NF];
+                long long item = blockIdx.x + (long long)(NA == 2 ? grp : 0) * gridDim.x;
+                if (item < items) load_row_thread<NF>(vn, Af, p.lda, p.M, (item / p.n_groups) * 128, p.K, ptid, wo);
+                for (uint32_t it = 0; item < items; item += step, it++) {
+                    float4 v[NF];
+#pragma unroll
+                    for (int i = 0; i < NF; i++) v[i] = vn[i];
+                    const long long m0 = (item / p.n_groups) * 128;
+                    if (item + step < items) load_row_thread<NF>(vn, Af, p.lda, p.M, ((item + step) / p.n_groups) * 128, p.K, ptid, wo);
+                    const uint32_t ab = NA == 2 ? grp : 0u;
+                    mbar_wait(&a_empty[ab], (it & 1u) ^ 1u);
+                    finish_row_thread<AMODE == AM_F32_LN, NF>(smem + L.a_off[ab], v, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
+                    fence_async_smem();
+                    mbar_arrive(&a_full[ab]);
+                }
+            };
+            run(std::integral_constant<int, 8>{});   // wider rows would spill at this CTA size: they take the plain loop below
+        } else if (!STREAM && (NA == 2 || grp == 0)) {
             uint32_t acount = 0;
             for (long long item = blockIdx.x; item < items; item += gridDim.x, acount++) {
                 const long long tile = item / p.n_groups;
@@ -577,7 +627,7 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                         if (p.bias) {
 #pragma unroll
                             for (int i = 0; i < 16; i += 4) {
-                                float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                                const float4 bb = *reinterpret_cast<const float4*>(sbias + n0 + i);
                                 v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
                             }
                         }
