@@ -83,17 +83,18 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
 static constexpr int TC_LN_PREPASS_MIN_C = 96;   // rows at least this wide are normalised by the pre-pass
 
 // ---- fused small-channel MLP (tc_mlp.cu) -------------------------------------------------------------
+// Persistent kernel with both weight matrices resident in shared memory; the hidden activation stays on chip.
 struct TcMlp {
     const float* x; const float* residual; float* out;
     long long M;
-    int C, Cpad, hidden, HC, n_hc;
+    int C, Cpad, hidden, Hpad;   // Cpad = pad16(C), Hpad = pad16(hidden)
     const float* ln_g; const float* ln_b; float eps;
-    const bf16* W1p;   // n_hc images [Cpad/8][HC][8]   (rows = hidden chunk)
-    const bf16* W2p;   // n_hc images [HC/8][Cpad][8]   (rows = output channel, k = hidden chunk)
-    const float* b1;   // [n_hc*HC] zero padded
-    const float* b2;   // [C]
+    const bf16* W1p;   // UMMA image [Cpad/8][Hpad][8]   (rows = hidden unit, k = input channel)
+    const bf16* W2p;   // UMMA image [Hpad/8][Cpad][8]   (rows = output channel, k = hidden unit)
+    const float* b1;   // [Hpad] zero padded
+    const float* b2;   // [Cpad] zero padded
 };
-int tc_mlp_pick_hc(int Cpad, int hidden);
+bool tc_mlp_supported(int C, int hidden);
 int launch_tc_mlp(const TcMlp& t, cudaStream_t st);
 
 // ---- attention core (attn_core.cu) ----------------------------------------------------------------------

@@ -207,8 +207,8 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
 }
 
 // =============================================================================================
-// MLP: GEMM1 (LN, +b1, ELU, bf16 UMMA-tiled hidden) + GEMM2 (bulk-copied A, +b2 +residual).
-// (tc_mlp.cu holds a fused single-kernel variant; see DESIGN.md for why it is not dispatched yet.)
+// MLP: narrow stages (C <= 64) run the fused persistent kernel of tc_mlp.cu (hidden activation stays on chip);
+// wider ones GEMM1 (LN, +b1, ELU, bf16 UMMA-tiled hidden) + GEMM2 (bulk-copied A, +b2 +residual).
 // =============================================================================================
 struct MlpPlan { PackedGemm g1, g2; bool prepass; size_t packed_bytes, off_h, off_packed, off_n, total; };
 
@@ -259,6 +259,16 @@ int mlp_fwd_bf16(const sf_mlp_params* p, void* ws_ptr, size_t ws_bytes, cudaStre
     if (!pk) {
         SF_TRY(mlp_pack_bf16(p, base + m.off_packed, m.packed_bytes, st));
         pk = base + m.off_packed;
+    }
+    if (tc_mlp_supported(p->C, p->hidden) && m.g1.nc == 1 && m.g2.nc == 1) {
+        TcMlp t{};
+        t.x = p->in; t.residual = p->residual; t.out = p->out; t.M = p->M;
+        t.C = p->C; t.Cpad = m.g1.kpad; t.hidden = p->hidden; t.Hpad = m.g1.nch;
+        t.ln_g = p->ln_gamma; t.ln_b = p->ln_beta; t.eps = p->ln_eps;
+        t.W1p = reinterpret_cast<const bf16*>(pk + m.g1.off_w); t.b1 = reinterpret_cast<const float*>(pk + m.g1.off_b);
+        t.W2p = reinterpret_cast<const bf16*>(pk + m.g2.off_w); t.b2 = reinterpret_cast<const float*>(pk + m.g2.off_b);
+        if (m.g2.nch != t.Cpad || m.g2.kpad != t.Hpad) { set_error("mlp: packed weight plan does not match the fused kernel"); return SF_ERR_INVALID; }
+        return launch_tc_mlp(t, st);
     }
     bf16* hid = reinterpret_cast<bf16*>(base + m.off_h);
     TcGemm g1{};

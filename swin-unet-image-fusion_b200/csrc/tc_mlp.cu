@@ -1,237 +1,323 @@
-// Fused MLP on tcgen05 (one CTA per 128-token tile): LN -> GEMM1 -> +b1 -> ELU -> bf16 back to smem
-// as the A operand of GEMM2, accumulated over hidden chunks in TMEM -> +b2 + residual.  The 4x
-// hidden activation never leaves the SM.  Used for the small-channel stages where that activation
-// would otherwise dominate HBM traffic.
-#include <initializer_list>
+// Fused MLP on tcgen05 for the narrow stages (a003:21-50):  out = x + W2 ELU(W1 LN(x) + b1) + b2.
+//
+// For C <= 64 the two GEMMs are HBM-bound and the 4x hidden activation dominates their traffic
+// (per token: 4C B in, 8C B hidden out, 8C B hidden in, 4C B residual, 4C B out).  Here the hidden
+// activation never leaves the SM: a persistent CTA per SM keeps both weight matrices resident in
+// shared memory and pipelines, tile (128 tokens) by tile, over double-buffered stages
+//
+//   warps 0-3    producers    fp32 rows -> LayerNorm -> bf16 A1 in the UMMA layout (one thread per row;
+//                             the next tile's rows are already in flight in registers)
+//   warp  4      MMA issuer   D1[128 x Hpad] = A1 W1^T ;  D2[128 x Cpad] = A2 W2^T   (tcgen05.mma, TMEM)
+//   warps 5-12   hidden       tcgen05.ld D1 -> +b1 -> ELU -> bf16 -> A2 (shared memory, UMMA layout)
+//   warps 13-16  output       tcgen05.ld D2 -> +b2 + residual -> fp32 rows
+//
+// mbarrier pipelines: A1 full/empty, D1 full/empty, A2 full/empty, D2 full/empty (all two deep), so
+// the producers run one tile ahead, GEMM1 of tile t+1 overlaps the ELU stage of tile t, and GEMM2 of
+// tile t overlaps the output stage of tile t-1.
+#include <type_traits>
 #include "bf16_kernels.cuh"
 #include "tc_common.cuh"
 
 namespace sf {
 using namespace tc;
 
-static constexpr uint32_t LBO_A = lbo_padded(128);
-static constexpr uint32_t SBO = 128;
-static constexpr int TC_THREADS = 128;
-static constexpr size_t SMEM_LIMIT = 227 * 1024;
-__host__ __device__ static inline uint32_t align128(uint32_t v) { return (v + 127) & ~127u; }
+static constexpr uint32_t LBO_A = lbo_padded(128);   // thread-written A operands: 2064 B between k-chunks
+static constexpr uint32_t SBO_M = 128;
+static constexpr int M_THREADS = 17 * 32;
+static constexpr int M_PW = 4;                       // producer warps; then 1 MMA warp, 8 hidden warps, 4 output warps
+static constexpr size_t M_SMEM_LIMIT = 227 * 1024;
+__host__ __device__ static inline uint32_t al128(uint32_t v) { return (v + 127) & ~127u; }
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-// fp32 rows (optionally LayerNorm-ed) -> bf16.  Lanes of a warp split into groups of LPR lanes,
-// one group per row, float4 per lane: global reads are coalesced and the row stays in registers
-// between the statistics and the normalisation.
-template <bool LN>
-__device__ __forceinline__ void produce_a_f32(uint8_t* sA, const float* __restrict__ A, long long lda, long long M, long long m0,
-                                              int K, int Kpad, const float* __restrict__ g, const float* __restrict__ b, float eps) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nf4 = K >> 2, nslots = Kpad >> 2;
-    int LPR = 1;
-    while (LPR < 32 && LPR < nslots) LPR <<= 1;
-    const int RPW = 32 / LPR;
-    const int gl = lane & (LPR - 1), gr = lane / LPR;
-    for (int it = 0; it < 32 / RPW; it++) {
-        const int r = warp * 32 + it * RPW + gr;
-        const long long m = m0 + r;
-        const bool rowok = m < M;
-        float4 v[3];
+struct MlpSmem { uint32_t w1, w2, a1[2], a2[2], b1, b2, bars, total; };
+__host__ __device__ static inline MlpSmem mlp_smem_layout(int Kpad, int Hpad, int N2) {
+    MlpSmem s{};
+    uint32_t o = 0;
+    s.w1 = o; o += al128((uint32_t)Hpad * Kpad * 2);
+    s.w2 = o; o += al128((uint32_t)N2 * Hpad * 2);
+    for (int i = 0; i < 2; i++) { s.a1[i] = o; o += al128((uint32_t)(Kpad >> 3) * LBO_A); }
+    for (int i = 0; i < 2; i++) { s.a2[i] = o; o += al128((uint32_t)(Hpad >> 3) * LBO_A); }
+    s.b1 = o; o += al128((uint32_t)Hpad * 4);
+    s.b2 = o; o += al128((uint32_t)N2 * 4);
+    s.bars = o; o += 256;
+    s.total = o;
+    return s;
+}
+
+// fp32 row (one thread per row) -> registers / registers -> [LayerNorm] -> bf16 UMMA chunks
+template <int NF>
+__device__ __forceinline__ void mlp_load_row(float4 (&v)[NF], const float* __restrict__ x, long long M, long long m, int C) {
+    const int nf4 = C >> 2;
+    const float4* src = reinterpret_cast<const float4*>(x + m * C);
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            int q = gl + i * LPR;
-            v[i] = (rowok && q < nf4) ? *reinterpret_cast<const float4*>(A + m * lda + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (LN) {
-            float s = 0.f;
+    for (int i = 0; i < NF; i++) v[i] = (m < M && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int NF>
+__device__ __forceinline__ void mlp_finish_row(uint8_t* sA, float4 (&v)[NF], int r, int C, int Kpad, const float* __restrict__ g,
+                                               const float* __restrict__ b, float eps) {
+    const int nf4 = C >> 2, nkc = Kpad >> 3;
+    if (g) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 3; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-            for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mean = s / (float)K;
-            float ss = 0.f;
+        for (int i = 0; i < NF; i++) { s0 += v[i].x + v[i].y; s1 += v[i].z + v[i].w; }
+        const float invk = 1.f / (float)C;
+        const float mean = (s0 + s1) * invk;
+        float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                if (gl + i * LPR < nf4) {
-                    float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
-                    ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-                }
-            }
-            for (int o = LPR >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            const float rstd = rsqrtf(ss / (float)K + eps);
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                int q = gl + i * LPR;
-                if (rowok && q < nf4) {
-                    float4 gg = __ldg(reinterpret_cast<const float4*>(g) + q), bb = __ldg(reinterpret_cast<const float4*>(b) + q);
-                    v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
-                    v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
-                    v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
-                    v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
-                }
+        for (int i = 0; i < NF; i++) {
+            if (i < nf4) {
+                float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                q0 += dx * dx + dy * dy; q1 += dz * dz + dw * dw;
             }
         }
+        const float rstd = rsqrtf((q0 + q1) * invk + eps);
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            int q = gl + i * LPR;
-            if (q < nslots) {
-                uint2 pk = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-                *reinterpret_cast<uint2*>(sA + (uint32_t)(q >> 1) * LBO_A + (uint32_t)r * 16 + (q & 1) * 8) = pk;
+        for (int i = 0; i < NF; i++) {
+            if (i < nf4) {
+                float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i), bb = __ldg(reinterpret_cast<const float4*>(b) + i);
+                v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
+                v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
+                v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
+                v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
             }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NF / 2; c++) {
+        if (c < nkc) {
+            uint4 pk = make_uint4(pack_bf16x2(v[2 * c].x, v[2 * c].y), pack_bf16x2(v[2 * c].z, v[2 * c].w),
+                                  pack_bf16x2(v[2 * c + 1].x, v[2 * c + 1].y), pack_bf16x2(v[2 * c + 1].z, v[2 * c + 1].w));
+            *reinterpret_cast<uint4*>(sA + (uint32_t)c * LBO_A + (uint32_t)r * 16) = pk;
         }
     }
 }
 
-// =============================================================================================
-// k_tc_mlp: out = residual + W2 ELU(W1 LN(x) + b1) + b2, hidden activation kept on chip
-// =============================================================================================
-
-template <bool LN>
-__global__ void __launch_bounds__(TC_THREADS) k_tc_mlp(TcMlp p) {
+__global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t Cpad = (uint32_t)p.Cpad, HC = (uint32_t)p.HC;
-    uint8_t* sA1 = smem;
-    uint8_t* sA2 = sA1 + align128((Cpad >> 3) * LBO_A);
-    uint8_t* sW1 = sA2 + align128((HC >> 3) * LBO_A);
-    const uint32_t w_bytes = HC * Cpad * 2u;  // both weight chunks have HC*Cpad elements
-    uint8_t* sW2 = sW1 + align128(w_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW2 + align128(w_bytes));  // w1, w2, mma1, mma2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-    const long long m0 = (long long)blockIdx.x * 128;
-    const uint32_t d2off = (HC + 31u) & ~31u;
-    const uint32_t ncols = tmem_cols_pow2(d2off + Cpad);
+    const int Kpad = p.Cpad, Hpad = p.Hpad, N2 = p.Cpad;
+    const MlpSmem L = mlp_smem_layout(Kpad, Hpad, N2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* a1_full = bars;        // [2]
+    uint64_t* a1_empty = bars + 2;   // [2]
+    uint64_t* d1_full = bars + 4;
+    uint64_t* d1_empty = bars + 6;
+    uint64_t* a2_full = bars + 8;
+    uint64_t* a2_empty = bars + 10;
+    uint64_t* d2_full = bars + 12;
+    uint64_t* d2_empty = bars + 14;
+    uint64_t* w_full = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    const uint32_t d1_stride = ((uint32_t)Hpad + 31u) & ~31u, d2_stride = ((uint32_t)N2 + 31u) & ~31u;
+    const uint32_t ncols = tmem_cols_pow2(2u * d1_stride + 2u * d2_stride);
+    const long long tiles = (p.M + 127) / 128;
+    const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t w1_bytes = (uint32_t)Hpad * Kpad * 2, w2_bytes = (uint32_t)N2 * Hpad * 2;
 
-    if (tid == 0) {
-        for (int i = 0; i < 4; i++) mbar_init(&bars[i], 1);
+    if (tid == M_PW * 32) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&a1_full[i], 128); mbar_init(&a1_empty[i], 1);
+            mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 8);
+            mbar_init(&a2_full[i], 8); mbar_init(&a2_empty[i], 1);
+            mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], 4);
+        }
+        mbar_init(w_full, 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&bars[0], w_bytes);
-        bulk_g2s(sW1, p.W1p, w_bytes, &bars[0]);
-        mbar_arrive_expect_tx(&bars[1], w_bytes);
-        bulk_g2s(sW2, p.W2p, w_bytes, &bars[1]);
+        // both weight matrices stay in shared memory for the life of the CTA
+        mbar_arrive_expect_tx(w_full, w1_bytes + w2_bytes);
+        bulk_g2s(smem + L.w1, p.W1p, w1_bytes, w_full);
+        bulk_g2s(smem + L.w2, p.W2p, w2_bytes, w_full);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, ncols);
-    produce_a_f32<LN>(sA1, p.x, p.C, p.M, m0, p.C, p.Cpad, p.ln_g, p.ln_b, p.eps);
-    fence_async_smem();
+    if (warp == M_PW + 1) tmem_alloc(tmem_slot, ncols);
+    {
+        float* sb1 = reinterpret_cast<float*>(smem + L.b1);
+        float* sb2 = reinterpret_cast<float*>(smem + L.b2);
+        for (int i = tid; i < Hpad; i += M_THREADS) sb1[i] = __ldg(p.b1 + i);
+        for (int i = tid; i < N2; i += M_THREADS) sb2[i] = __ldg(p.b2 + i);
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), w1 = smem_u32(sW1), w2 = smem_u32(sW2);
-    const int row = warp * 32 + lane;
-    const long long m = m0 + row;
-    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float* sb1 = reinterpret_cast<const float*>(smem + L.b1);
+    const float* sb2 = reinterpret_cast<const float*>(smem + L.b2);
 
-    for (int hc = 0; hc < p.n_hc; hc++) {
-        const uint32_t par = (uint32_t)hc & 1u;
-        if (tid == 0) {  // GEMM1: D1[128 x HC] = A1 * W1chunk^T
-            mbar_wait(&bars[0], par);
-            tc_fence_after_sync();
-            const uint32_t idesc = make_idesc_bf16(128, HC);
-            const uint32_t lbo_w = lbo_dense(HC);
-            for (uint32_t ks = 0; ks < (Cpad >> 4); ks++)
-                umma_bf16(tmem_base, make_smem_desc(a1 + ks * 2u * LBO_A, LBO_A, SBO), make_smem_desc(w1 + ks * 2u * lbo_w, lbo_w, SBO), idesc, ks > 0);
-            umma_commit(&bars[2]);
-        }
-        mbar_wait(&bars[2], par);
-        tc_fence_after_sync();
-        if (hc > 0) {  // GEMM2 of the previous chunk must be done before sA2 / sW2 are overwritten
-            mbar_wait(&bars[3], par ^ 1u);
-            tc_fence_after_sync();
-        }
-        if (tid == 0) {
-            if (hc + 1 < p.n_hc) {  // sW1 is free (GEMM1 done): prefetch the next W1 chunk
-                mbar_arrive_expect_tx(&bars[0], w_bytes);
-                bulk_g2s(sW1, p.W1p + (size_t)(hc + 1) * HC * Cpad, w_bytes, &bars[0]);
-            }
-            if (hc > 0) {  // sW2 is free: fetch this chunk's W2 (it lands while the ELU epilogue runs)
-                mbar_arrive_expect_tx(&bars[1], w_bytes);
-                bulk_g2s(sW2, p.W2p + (size_t)hc * HC * Cpad, w_bytes, &bars[1]);
-            }
-        }
-        __syncwarp();
-        // epilogue 1: D1 -> +b1 -> ELU -> bf16 -> sA2 (A operand of GEMM2)
-        for (uint32_t c16 = 0; c16 < HC; c16 += 16) {
-            float v[16];
-            tmem_ld16(tlane + c16, v);
-            const float* bb = p.b1 + (size_t)hc * HC + c16;
+    if (warp < M_PW) {
+        // ------------------------------ producers ---------------------------------------------------------
+        const int r = tid;
+        auto run = [&](auto tag, auto pre) {
+            constexpr int NF = decltype(tag)::value;
+            constexpr bool PREFETCH = decltype(pre)::value;
+            float4 vn[NF];
+            if (PREFETCH && my_tiles > 0) mlp_load_row<NF>(vn, p.x, p.M, (long long)blockIdx.x * 128 + r, p.C);
+            for (long long t = 0; t < my_tiles; t++) {
+                const long long tile = blockIdx.x + t * gridDim.x;
+                float4 v[NF];
+                if (PREFETCH) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = elu1(v[i] + __ldg(bb + i));
-            uint8_t* dst = sA2 + (c16 >> 3) * LBO_A + (uint32_t)row * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            *reinterpret_cast<uint4*>(dst + LBO_A) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-        }
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        tc_fence_after_sync();
-        if (tid == 0) {  // GEMM2: D2[128 x Cpad] += A2 * W2chunk^T   (N split in <=256-wide pieces)
-            mbar_wait(&bars[1], par);
-            tc_fence_after_sync();
-            const uint32_t lbo_w = lbo_dense(Cpad);
-            for (uint32_t n0 = 0; n0 < Cpad; n0 += 256) {
-                const uint32_t nsz = (Cpad - n0) < 256u ? (Cpad - n0) : 256u;
-                const uint32_t idesc = make_idesc_bf16(128, nsz);
-                for (uint32_t ks = 0; ks < (HC >> 4); ks++)
-                    umma_bf16(tmem_base + d2off + n0, make_smem_desc(a2 + ks * 2u * LBO_A, LBO_A, SBO),
-                              make_smem_desc(w2 + ks * 2u * lbo_w + n0 * 16u, lbo_w, SBO), idesc, hc > 0 || ks > 0);
+                    for (int i = 0; i < NF; i++) v[i] = vn[i];
+                    if (t + 1 < my_tiles) mlp_load_row<NF>(vn, p.x, p.M, (tile + gridDim.x) * 128 + r, p.C);
+                } else {
+                    mlp_load_row<NF>(v, p.x, p.M, tile * 128 + r, p.C);
+                }
+                const uint32_t b = (uint32_t)t & 1u;
+                mbar_wait(&a1_empty[b], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                mlp_finish_row<NF>(smem + L.a1[b], v, r, p.C, Kpad, p.ln_g, p.ln_b, p.eps);
+                fence_async_smem();
+                mbar_arrive1(&a1_full[b]);
             }
-            umma_commit(&bars[3]);
+        };
+        if (Kpad <= 32) run(std::integral_constant<int, 8>{}, std::true_type{});
+        else run(std::integral_constant<int, 16>{}, std::false_type{});
+    } else if (warp == M_PW) {
+        // ------------------------------ MMA issuer --------------------------------------------------------
+        if (lane == 0 && my_tiles > 0) {
+            mbar_wait(w_full, 0);
+            tc_fence_after_sync();
+            const uint32_t idesc1 = make_idesc_bf16(128, (uint32_t)Hpad), idesc2 = make_idesc_bf16(128, (uint32_t)N2);
+            const uint32_t lbo_w1 = lbo_dense((uint32_t)Hpad), lbo_w2 = lbo_dense((uint32_t)N2);
+            const uint32_t w1 = smem_u32(smem + L.w1), w2 = smem_u32(smem + L.w2);
+            auto gemm1 = [&](long long t) {
+                const uint32_t b = (uint32_t)t & 1u, par = ((uint32_t)t >> 1) & 1u;
+                mbar_wait(&a1_full[b], par);
+                mbar_wait(&d1_empty[b], par ^ 1u);
+                tc_fence_after_sync();
+                const uint32_t a = smem_u32(smem + L.a1[b]);
+                for (int ks = 0; ks < (Kpad >> 4); ks++)
+                    umma_bf16(tmem_base + b * d1_stride, make_smem_desc(a + (uint32_t)ks * 2u * LBO_A, LBO_A, SBO_M),
+                              make_smem_desc(w1 + (uint32_t)ks * 2u * lbo_w1, lbo_w1, SBO_M), idesc1, ks > 0);
+                umma_commit(&a1_empty[b]);
+                umma_commit(&d1_full[b]);
+            };
+            auto gemm2 = [&](long long t) {
+                const uint32_t b = (uint32_t)t & 1u, par = ((uint32_t)t >> 1) & 1u;
+                mbar_wait(&a2_full[b], par);
+                mbar_wait(&d2_empty[b], par ^ 1u);
+                tc_fence_after_sync();
+                const uint32_t a = smem_u32(smem + L.a2[b]);
+                for (int ks = 0; ks < (Hpad >> 4); ks++)
+                    umma_bf16(tmem_base + 2u * d1_stride + b * d2_stride, make_smem_desc(a + (uint32_t)ks * 2u * LBO_A, LBO_A, SBO_M),
+                              make_smem_desc(w2 + (uint32_t)ks * 2u * lbo_w2, lbo_w2, SBO_M), idesc2, ks > 0);
+                umma_commit(&a2_empty[b]);
+                umma_commit(&d2_full[b]);
+            };
+            gemm1(0);
+            for (long long t = 0; t < my_tiles; t++) {
+                if (t + 1 < my_tiles) gemm1(t + 1);
+                gemm2(t);
+            }
         }
-    }
-    mbar_wait(&bars[3], (uint32_t)(p.n_hc - 1) & 1u);
-    __syncwarp();
-    tc_fence_after_sync();
-    // epilogue 2: D2 + b2 + residual -> out (fp32)
-    for (uint32_t c16 = 0; c16 < Cpad; c16 += 16) {
-        if ((int)c16 >= p.C) break;
-        float v[16];
-        tmem_ld16(tlane + d2off + c16, v);
-        if (m < p.M) {
-            float* o = p.out + m * p.C + c16;
-            const float* rs = p.residual ? p.residual + m * p.C + c16 : nullptr;
+    } else if (warp < M_PW + 1 + 8) {
+        // ------------------------------ hidden stage: D1 -> +b1 -> ELU -> bf16 A2 -----------------------------
+        const int rb = warp & 3, eg = (warp - (M_PW + 1)) >> 2;
+        const int row = rb * 32 + lane;
+        for (long long t = 0; t < my_tiles; t++) {
+            const uint32_t b = (uint32_t)t & 1u, par = ((uint32_t)t >> 1) & 1u;
+            mbar_wait(&d1_full[b], par);
+            mbar_wait(&a2_empty[b], par ^ 1u);
+            __syncwarp();
+            tc_fence_after_sync();
+            const uint32_t tlane = tmem_base + b * d1_stride + ((uint32_t)(rb * 32) << 16);
+            uint8_t* sA2 = smem + L.a2[b];
+            for (int c16 = eg * 16; c16 < Hpad; c16 += 32) {
+                float v[16];
+                tmem_ld16(tlane + (uint32_t)c16, v);
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                if ((int)c16 + i + 4 <= p.C) {
-                    float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + c16 + i));
-                    float4 t = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
-                    if (rs) {
-                        float4 rr = *reinterpret_cast<const float4*>(rs + i);
-                        t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sb1 + c16 + i);
+                    v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;
+                uint8_t* dst = sA2 + (uint32_t)(c16 >> 3) * LBO_A + (uint32_t)row * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                *reinterpret_cast<uint4*>(dst + LBO_A) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive1(&d1_empty[b]); mbar_arrive1(&a2_full[b]); }
+        }
+    } else {
+        // ------------------------------ output stage: D2 + b2 + residual -> fp32 rows --------------------------
+        const int rb = warp & 3;
+        const int row = rb * 32 + lane;
+        for (long long t = 0; t < my_tiles; t++) {
+            const long long tile = blockIdx.x + t * gridDim.x;
+            const long long m = tile * 128 + row;
+            const uint32_t b = (uint32_t)t & 1u, par = ((uint32_t)t >> 1) & 1u;
+            // the residual row is in flight while the accumulator is awaited
+            float4 rr[16];
+            const bool rowok = m < p.M;
+            const int nf4 = p.C >> 2;
+            if (p.residual) {
+                const float4* rs = reinterpret_cast<const float4*>(p.residual + m * p.C);
+#pragma unroll
+                for (int i = 0; i < 16; i++) rr[i] = (rowok && i < nf4) ? rs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_wait(&d2_full[b], par);
+            __syncwarp();
+            tc_fence_after_sync();
+            const uint32_t tlane = tmem_base + 2u * d1_stride + b * d2_stride + ((uint32_t)(rb * 32) << 16);
+#pragma unroll
+            for (int g16 = 0; g16 < 4; g16++) {
+                const int c16 = g16 * 16;
+                if (c16 < p.C) {   // uniform
+                    float v[16];
+                    tmem_ld16(tlane + (uint32_t)c16, v);
+                    if (rowok) {
+                        float* o = p.out + m * p.C + c16;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            if (c16 + i + 4 <= p.C) {
+                                const float4 bb = *reinterpret_cast<const float4*>(sb2 + c16 + i);
+                                const float4 q4 = rr[g16 * 4 + (i >> 2)];
+                                *reinterpret_cast<float4*>(o + i) =
+                                    make_float4(v[i] + bb.x + q4.x, v[i + 1] + bb.y + q4.y, v[i + 2] + bb.z + q4.z, v[i + 3] + bb.w + q4.w);
+                            }
+                        }
                     }
-                    *reinterpret_cast<float4*>(o + i) = t;
                 }
             }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&d2_empty[b]);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+    if (warp == M_PW + 1) tmem_dealloc(tmem_base, ncols);
 }
 
-static size_t tc_mlp_smem(int Cpad, int HC) {
-    return align128((uint32_t)(Cpad / 8) * LBO_A) + align128((uint32_t)(HC / 8) * LBO_A) + 2 * (size_t)align128((uint32_t)HC * Cpad * 2) + 64;
+bool tc_mlp_supported(int C, int hidden) {
+    if (C % 4 != 0 || C > 64 || hidden < 1) return false;
+    const int Kpad = (int)pad16((uint32_t)C), Hpad = (int)pad16((uint32_t)hidden);
+    if (Hpad > 256) return false;
+    const uint32_t cols = 2u * (((uint32_t)Hpad + 31u) & ~31u) + 2u * (((uint32_t)Kpad + 31u) & ~31u);
+    return cols <= 512 && mlp_smem_layout(Kpad, Hpad, Kpad).total <= M_SMEM_LIMIT;
 }
-
-int tc_mlp_pick_hc(int Cpad, int hidden) {
-    int hpad = (int)pad16((uint32_t)hidden);
-    for (int hc : {128, 64, 32, 16}) {
-        if (hc > hpad && hc != 16) continue;
-        if (tc_mlp_smem(Cpad, hc) <= SMEM_LIMIT && ((hc + 31) / 32 * 32 + Cpad) <= 512) return hc;
-    }
-    return 0;
-}
-
 
 int launch_tc_mlp(const TcMlp& t, cudaStream_t st) {
-    size_t smem = tc_mlp_smem(t.Cpad, t.HC);
+    SF_CHECK_ARG(tc_mlp_supported(t.C, t.hidden), "tc_mlp: unsupported shape C=%d hidden=%d", t.C, t.hidden);
+    const MlpSmem L = mlp_smem_layout(t.Cpad, t.Hpad, t.Cpad);
     static thread_local bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(k_tc_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-        cudaError_t e2 = cudaFuncSetAttribute(k_tc_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("tc_mlp: cudaFuncSetAttribute failed"); return SF_ERR_CUDA; }
+        cudaError_t e = cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM_LIMIT);
+        if (e != cudaSuccess) { set_error("tc_mlp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
         configured = true;
     }
-    long long tiles = (t.M + 127) / 128;
-    SF_CHECK_ARG(tiles <= 2147483647LL, "tc_mlp: M too large");
-    ProfScope ps("tc_mlp_fused", 4.0 * (double)t.M * t.C * t.hidden,
+    const long long tiles = (t.M + 127) / 128;
+    long long grid = 148;
+    if (grid > tiles) grid = tiles;
+    // algorithmic work: two GEMMs; bytes: x in, residual in (when it is another tensor), out, weights once
+    ProfScope ps(prof_name("tc_mlp_fused_c%d", t.C), 4.0 * (double)t.M * t.C * t.hidden,
                  4.0 * (double)t.M * t.C * (t.residual && t.residual != t.x ? 3.0 : 2.0) + 4.0 * t.C * t.hidden, st);
-    if (t.ln_g) k_tc_mlp<true><<<(unsigned)tiles, TC_THREADS, smem, st>>>(t);
-    else k_tc_mlp<false><<<(unsigned)tiles, TC_THREADS, smem, st>>>(t);
+    k_tc_mlp<<<(unsigned)grid, M_THREADS, L.total, st>>>(t);
     SF_CHECK_LAUNCH("tc_mlp");
     return SF_OK;
 }

@@ -25,7 +25,9 @@ def _bf16_default():
 
 
 @pytest.mark.parametrize("m,c,hidden", [(300, 24, 96), (1000, 48, 192), (257, 96, 384), (130, 192, 768), (128, 384, 1536),
-                                        (77, 24, 4), (500, 16, 40)])
+                                        (77, 24, 4), (500, 16, 40),
+                                        # persistent fused kernel: several tiles per CTA (barrier phases wrap), ragged tail
+                                        (148 * 128 * 3 + 77, 24, 96), (148 * 128 * 2 + 5, 48, 192), (148 * 128 * 5 + 1, 64, 256)])
 def test_fused_mlp_tcgen05(m, c, hidden):
     sw = dropin()
     g = torch.Generator().manual_seed(m + c)
