@@ -45,6 +45,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();
     }
 }
+// Same, for the many-thread stages (producers, epilogues): a failed probe backs off for a few tens of
+// nanoseconds so that waiting warps do not take issue slots from the warps they are waiting for.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(40);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+// ELU(alpha = 1) on the fast path: exp through ex2.approx.ftz (2^-22 relative), no denormal range fix-up
+__device__ __forceinline__ float elu_fast(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    return v > 0.f ? v : e - 1.f;
+}
 
 // ---- proxies / fences ----------------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)

@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                     const long long m0 = (item / p.n_groups) * 128;
                     if (item + step < items) load_row_thread<NF>(vn, Af, p.lda, p.M, ((item + step) / p.n_groups) * 128, p.K, ptid, wo);
                     const uint32_t ab = NA == 2 ? grp : 0u;
-                    mbar_wait(&a_empty[ab], (it & 1u) ^ 1u);
+                    mbar_wait_relaxed(&a_empty[ab], (it & 1u) ^ 1u);
                     finish_row_thread<AMODE == AM_F32_LN, NF>(smem + L.a_off[ab], v, p.M, m0, p.K, p.Kpad, p.ln_g, p.ln_b, p.eps, ptid);
                     fence_async_smem();
                     mbar_arrive(&a_full[ab]);
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                 const long long tile = item / p.n_groups;
                 const uint32_t ab = acount % (uint32_t)NA;
                 if (NA == 2 && ab != grp) continue;
-                mbar_wait(&a_empty[ab], ((acount / (uint32_t)NA) & 1u) ^ 1u);
+                mbar_wait_relaxed(&a_empty[ab], ((acount / (uint32_t)NA) & 1u) ^ 1u);
                 uint8_t* sA = smem + L.a_off[ab];
                 if (AMODE == AM_F32_LN) produce_a_f32<true>(sA, p, tile * 128, ptid);
                 else if (AMODE == AM_F32) produce_a_f32<false>(sA, p, tile * 128, ptid);
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
             const int c1 = min(c0 + p.chunks_per_group, p.n_chunks);
             for (int c = c0; c < c1; c++, tcount++) {
                 const uint32_t acc = tcount & 1u;
-                mbar_wait(&d_full[acc], (tcount >> 1) & 1u);
+                mbar_wait_relaxed(&d_full[acc], (tcount >> 1) & 1u);
                 __syncwarp();
                 tc_fence_after_sync();
                 const uint32_t tlane = tmem_base + acc * acc_stride + ((uint32_t)(rb * 32) << 16);
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                         }
                         if (p.elu) {
 #pragma unroll
-                            for (int i = 0; i < 16; i++) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;
+                            for (int i = 0; i < 16; i++) v[i] = elu_fast(v[i]);
                         }
                         if (OUTMODE == OUT_TILED) {
                             // chunk (tile, kc, r) at ((tile*out_nkc + kc)*128 + r)*8 elements; columns >= N are zero

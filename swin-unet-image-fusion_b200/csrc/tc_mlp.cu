@@ -5,8 +5,11 @@
 // activation never leaves the SM: a persistent CTA per SM keeps both weight matrices resident in
 // shared memory and pipelines, tile (128 tokens) by tile, over double-buffered stages
 //
-//   warps 0-3    producers    fp32 rows -> LayerNorm -> bf16 A1 in the UMMA layout (one thread per row;
-//                             the next tile's rows are already in flight in registers)
+//   warp  17     loader       one cp.async.bulk per tile: the 128 fp32 rows (contiguous) -> a ring of raw tiles in
+//                             shared memory, several tiles ahead (HBM latency is covered by the ring depth, not
+//                             by registers); with a deep ring the tile is kept until the output stage has
+//                             taken the residual from it, so x is read from HBM exactly once
+//   warps 0-3    producers    raw row (one thread per row) -> LayerNorm -> bf16 A1 in the UMMA layout
 //   warp  4      MMA issuer   D1[128 x Hpad] = A1 W1^T ;  D2[128 x Cpad] = A2 W2^T   (tcgen05.mma, TMEM)
 //   warps 5-12   hidden       tcgen05.ld D1 -> +b1 -> ELU -> bf16 -> A2 (shared memory, UMMA layout)
 //   warps 13-16  output       tcgen05.ld D2 -> +b2 + residual -> fp32 rows
@@ -23,7 +26,10 @@ using namespace tc;
 
 static constexpr uint32_t LBO_A = lbo_padded(128);   // thread-written A operands: 2064 B between k-chunks
 static constexpr uint32_t SBO_M = 128;
-static constexpr int M_THREADS = 17 * 32;
+static constexpr int M_THREADS = 18 * 32;
+static constexpr int M_LOADER = 17;                  // loader warp
+static constexpr int M_MAX_STAGES = 8;
+static constexpr int M_RES_MIN_STAGES = 5;           // ring deep enough to hold a tile until its output stage: residual from the ring
 static constexpr int M_PW = 4;                       // producer warps; then 1 MMA warp, 8 hidden warps, 4 output warps
 static constexpr size_t M_SMEM_LIMIT = 227 * 1024;
 __host__ __device__ static inline uint32_t al128(uint32_t v) { return (v + 127) & ~127u; }
@@ -31,8 +37,8 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct MlpSmem { uint32_t w1, w2, a1[2], a2[2], b1, b2, bars, total; };
-__host__ __device__ static inline MlpSmem mlp_smem_layout(int Kpad, int Hpad, int N2) {
+struct MlpSmem { uint32_t w1, w2, a1[2], a2[2], b1, b2, bars, ring, tile_bytes, nstage, total; };
+__host__ __device__ static inline MlpSmem mlp_smem_layout(int Kpad, int Hpad, int N2, int C) {
     MlpSmem s{};
     uint32_t o = 0;
     s.w1 = o; o += al128((uint32_t)Hpad * Kpad * 2);
@@ -41,18 +47,23 @@ __host__ __device__ static inline MlpSmem mlp_smem_layout(int Kpad, int Hpad, in
     for (int i = 0; i < 2; i++) { s.a2[i] = o; o += al128((uint32_t)(Hpad >> 3) * LBO_A); }
     s.b1 = o; o += al128((uint32_t)Hpad * 4);
     s.b2 = o; o += al128((uint32_t)N2 * 4);
-    s.bars = o; o += 256;
-    s.total = o;
+    s.bars = o; o += 384;
+    s.ring = o;
+    s.tile_bytes = al128(128u * (uint32_t)C * 4u);
+    const uint32_t room = o < (uint32_t)M_SMEM_LIMIT ? (uint32_t)M_SMEM_LIMIT - o : 0u;
+    s.nstage = room / s.tile_bytes;
+    if (s.nstage > (uint32_t)M_MAX_STAGES) s.nstage = M_MAX_STAGES;
+    s.total = o + s.nstage * s.tile_bytes;
     return s;
 }
 
 // fp32 row (one thread per row) -> registers / registers -> [LayerNorm] -> bf16 UMMA chunks
 template <int NF>
-__device__ __forceinline__ void mlp_load_row(float4 (&v)[NF], const float* __restrict__ x, long long M, long long m, int C) {
+__device__ __forceinline__ void mlp_load_row(float4 (&v)[NF], const uint8_t* raw_tile, int r, bool rowok, int C) {
     const int nf4 = C >> 2;
-    const float4* src = reinterpret_cast<const float4*>(x + m * C);
+    const float4* src = reinterpret_cast<const float4*>(raw_tile + (size_t)r * C * 4);
 #pragma unroll
-    for (int i = 0; i < NF; i++) v[i] = (m < M && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NF; i++) v[i] = (rowok && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 template <int NF>
 __device__ __forceinline__ void mlp_finish_row(uint8_t* sA, float4 (&v)[NF], int r, int C, int Kpad, const float* __restrict__ g,
@@ -98,7 +109,10 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Kpad = p.Cpad, Hpad = p.Hpad, N2 = p.Cpad;
-    const MlpSmem L = mlp_smem_layout(Kpad, Hpad, N2);
+    const MlpSmem L = mlp_smem_layout(Kpad, Hpad, N2, p.C);
+    const uint32_t NS = L.nstage;
+    // the residual is x itself (a003 through a004:29-38) and the ring is deep enough: take it from the ring
+    const bool ring_res = p.residual == p.x && NS >= (uint32_t)M_RES_MIN_STAGES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* a1_full = bars;        // [2]
     uint64_t* a1_empty = bars + 2;   // [2]
@@ -109,7 +123,9 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
     uint64_t* d2_full = bars + 12;
     uint64_t* d2_empty = bars + 14;
     uint64_t* w_full = bars + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* x_full = bars + 17;    // [M_MAX_STAGES]
+    uint64_t* x_empty = bars + 25;   // [M_MAX_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
     const uint32_t d1_stride = ((uint32_t)Hpad + 31u) & ~31u, d2_stride = ((uint32_t)N2 + 31u) & ~31u;
     const uint32_t ncols = tmem_cols_pow2(2u * d1_stride + 2u * d2_stride);
     const long long tiles = (p.M + 127) / 128;
@@ -124,6 +140,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
             mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], 4);
         }
         mbar_init(w_full, 1);
+        for (uint32_t i = 0; i < NS; i++) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], ring_res ? 128 + 4 : 128); }
         fence_mbar_init();
         // both weight matrices stay in shared memory for the life of the CTA
         mbar_arrive_expect_tx(w_full, w1_bytes + w2_bytes);
@@ -147,30 +164,37 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
     if (warp < M_PW) {
         // ------------------------------ producers ---------------------------------------------------------
         const int r = tid;
-        auto run = [&](auto tag, auto pre) {
+        auto run = [&](auto tag) {
             constexpr int NF = decltype(tag)::value;
-            constexpr bool PREFETCH = decltype(pre)::value;
-            float4 vn[NF];
-            if (PREFETCH && my_tiles > 0) mlp_load_row<NF>(vn, p.x, p.M, (long long)blockIdx.x * 128 + r, p.C);
             for (long long t = 0; t < my_tiles; t++) {
                 const long long tile = blockIdx.x + t * gridDim.x;
+                const uint32_t st = (uint32_t)(t % NS), sp = (uint32_t)((t / NS) & 1);
                 float4 v[NF];
-                if (PREFETCH) {
-#pragma unroll
-                    for (int i = 0; i < NF; i++) v[i] = vn[i];
-                    if (t + 1 < my_tiles) mlp_load_row<NF>(vn, p.x, p.M, (tile + gridDim.x) * 128 + r, p.C);
-                } else {
-                    mlp_load_row<NF>(v, p.x, p.M, tile * 128 + r, p.C);
-                }
+                mbar_wait_relaxed(&x_full[st], sp);
+                mlp_load_row<NF>(v, smem + L.ring + st * L.tile_bytes, r, tile * 128 + r < p.M, p.C);
+                mbar_arrive1(&x_empty[st]);   // (with ring_res the output stage holds the slot a little longer)
                 const uint32_t b = (uint32_t)t & 1u;
-                mbar_wait(&a1_empty[b], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                mbar_wait_relaxed(&a1_empty[b], (((uint32_t)t >> 1) & 1u) ^ 1u);
                 mlp_finish_row<NF>(smem + L.a1[b], v, r, p.C, Kpad, p.ln_g, p.ln_b, p.eps);
                 fence_async_smem();
                 mbar_arrive1(&a1_full[b]);
             }
         };
-        if (Kpad <= 32) run(std::integral_constant<int, 8>{}, std::true_type{});
-        else run(std::integral_constant<int, 16>{}, std::false_type{});
+        if (Kpad <= 32) run(std::integral_constant<int, 8>{});
+        else run(std::integral_constant<int, 16>{});
+    } else if (warp == M_LOADER) {
+        // ------------------------------ loader: raw fp32 tiles -> ring ------------------------------------------
+        if (lane == 0) {
+            for (long long t = 0; t < my_tiles; t++) {
+                const long long tile = blockIdx.x + t * gridDim.x;
+                const uint32_t st = (uint32_t)(t % NS), sp = (uint32_t)((t / NS) & 1);
+                mbar_wait(&x_empty[st], sp ^ 1u);
+                const long long rows = (p.M - tile * 128) < 128 ? (p.M - tile * 128) : 128;
+                const uint32_t bytes = (uint32_t)rows * (uint32_t)p.C * 4u;
+                mbar_arrive_expect_tx(&x_full[st], bytes);
+                bulk_g2s(smem + L.ring + st * L.tile_bytes, p.x + tile * 128 * p.C, bytes, &x_full[st]);
+            }
+        }
     } else if (warp == M_PW) {
         // ------------------------------ MMA issuer --------------------------------------------------------
         if (lane == 0 && my_tiles > 0) {
@@ -209,14 +233,14 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
                 gemm2(t);
             }
         }
-    } else if (warp < M_PW + 1 + 8) {
+    } else if (warp >= M_PW + 1 && warp < M_PW + 1 + 8) {
         // ------------------------------ hidden stage: D1 -> +b1 -> ELU -> bf16 A2 -----------------------------
         const int rb = warp & 3, eg = (warp - (M_PW + 1)) >> 2;
         const int row = rb * 32 + lane;
         for (long long t = 0; t < my_tiles; t++) {
             const uint32_t b = (uint32_t)t & 1u, par = ((uint32_t)t >> 1) & 1u;
-            mbar_wait(&d1_full[b], par);
-            mbar_wait(&a2_empty[b], par ^ 1u);
+            mbar_wait_relaxed(&d1_full[b], par);
+            mbar_wait_relaxed(&a2_empty[b], par ^ 1u);
             __syncwarp();
             tc_fence_after_sync();
             const uint32_t tlane = tmem_base + b * d1_stride + ((uint32_t)(rb * 32) << 16);
@@ -230,7 +254,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
                     v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
                 }
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;
+                for (int i = 0; i < 16; i++) v[i] = elu_fast(v[i]);
                 uint8_t* dst = sA2 + (uint32_t)(c16 >> 3) * LBO_A + (uint32_t)row * 16;
                 *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                 *reinterpret_cast<uint4*>(dst + LBO_A) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
@@ -240,7 +264,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
             __syncwarp();
             if (lane == 0) { mbar_arrive1(&d1_empty[b]); mbar_arrive1(&a2_full[b]); }
         }
-    } else {
+    } else if (warp >= M_PW + 9 && warp < M_PW + 13) {
         // ------------------------------ output stage: D2 + b2 + residual -> fp32 rows --------------------------
         const int rb = warp & 3;
         const int row = rb * 32 + lane;
@@ -248,11 +272,20 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
             const long long tile = blockIdx.x + t * gridDim.x;
             const long long m = tile * 128 + row;
             const uint32_t b = (uint32_t)t & 1u, par = ((uint32_t)t >> 1) & 1u;
-            // the residual row is in flight while the accumulator is awaited
+            // the residual row: from the ring (x itself, read once from HBM) or in flight from global while the
+            // accumulator is awaited
             float4 rr[16];
             const bool rowok = m < p.M;
             const int nf4 = p.C >> 2;
-            if (p.residual) {
+            if (ring_res) {
+                const uint32_t st = (uint32_t)(t % NS), sp = (uint32_t)((t / NS) & 1);
+                mbar_wait_relaxed(&x_full[st], sp);   // completed long ago; makes the bulk-copied bytes visible to this thread
+                const float4* rs = reinterpret_cast<const float4*>(smem + L.ring + st * L.tile_bytes + (size_t)row * p.C * 4);
+#pragma unroll
+                for (int i = 0; i < 16; i++) rr[i] = (rowok && i < nf4) ? rs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                if (lane == 0) mbar_arrive1(&x_empty[st]);
+            } else if (p.residual) {
                 const float4* rs = reinterpret_cast<const float4*>(p.residual + m * p.C);
 #pragma unroll
                 for (int i = 0; i < 16; i++) rr[i] = (rowok && i < nf4) ? rs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -260,7 +293,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            mbar_wait(&d2_full[b], par);
+            mbar_wait_relaxed(&d2_full[b], par);
             __syncwarp();
             tc_fence_after_sync();
             const uint32_t tlane = tmem_base + 2u * d1_stride + b * d2_stride + ((uint32_t)(rb * 32) << 16);
@@ -299,12 +332,13 @@ bool tc_mlp_supported(int C, int hidden) {
     const int Kpad = (int)pad16((uint32_t)C), Hpad = (int)pad16((uint32_t)hidden);
     if (Hpad > 256) return false;
     const uint32_t cols = 2u * (((uint32_t)Hpad + 31u) & ~31u) + 2u * (((uint32_t)Kpad + 31u) & ~31u);
-    return cols <= 512 && mlp_smem_layout(Kpad, Hpad, Kpad).total <= M_SMEM_LIMIT;
+    const MlpSmem L = mlp_smem_layout(Kpad, Hpad, Kpad, C);
+    return cols <= 512 && L.nstage >= 2 && L.total <= M_SMEM_LIMIT;
 }
 
 int launch_tc_mlp(const TcMlp& t, cudaStream_t st) {
     SF_CHECK_ARG(tc_mlp_supported(t.C, t.hidden), "tc_mlp: unsupported shape C=%d hidden=%d", t.C, t.hidden);
-    const MlpSmem L = mlp_smem_layout(t.Cpad, t.Hpad, t.Cpad);
+    const MlpSmem L = mlp_smem_layout(t.Cpad, t.Hpad, t.Cpad, t.C);
     static thread_local bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM_LIMIT);
