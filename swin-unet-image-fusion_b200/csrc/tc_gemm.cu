@@ -327,33 +327,54 @@ __device__ __forceinline__ void produce_a_f32(uint8_t* sA, const TcGemm& p, long
 }
 
 // patch-merge gather (a011:87-93): row (b,Y,X), k = (ph*mw+pw)*Cin + c <- in[b][Y*mh+ph][X*mw+pw][c]
+// One thread per row: the row's pixel coordinates are decoded once; with Cin % 8 == 0 every 8-element
+// k-chunk is 8 consecutive channels of one source pixel (two 16-byte loads).
 __device__ __forceinline__ void produce_a_merge(uint8_t* sA, const TcGemm& p, long long m0, int ptid) {
     const float* __restrict__ in = reinterpret_cast<const float*>(p.A);
     const int nkc = p.Kpad >> 3;
     const int Hc = p.Hf / p.mh, Wc = p.Wf / p.mw;
-    for (int idx = ptid; idx < 128 * nkc; idx += 128) {
-        int kc = idx >> 7, r = idx & 127;  // consecutive threads -> consecutive rows (conflict-free st.shared)
-        long long m = m0 + r;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = 0.f;
-        if (m < p.M) {
-            int X = (int)(m % Wc);
-            long long t = m / Wc;
-            int Y = (int)(t % Hc);
-            long long b = t / Hc;
+    const int r = ptid;
+    const long long m = m0 + r;
+    const bool rowok = m < p.M;
+    int X = 0, Y = 0;
+    long long b = 0;
+    if (rowok) {
+        X = (int)(m % Wc);
+        long long t = m / Wc;
+        Y = (int)(t % Hc);
+        b = t / Hc;
+    }
+    const float* base = in + ((b * p.Hf + (long long)Y * p.mh) * p.Wf + (long long)X * p.mw) * p.Cin;   // pixel (ph, pw) = (0, 0)
+    const long long rowpitch = (long long)p.Wf * p.Cin;
+    if ((p.Cin & 7) == 0) {
+        const int cpp = p.Cin >> 3;   // chunks per source pixel
+        int q = 0, cc = 0, ph = 0, pw = 0;
+        for (int kc = 0; kc < nkc; kc++) {
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (rowok && kc * 8 < p.K) {
+                const float4* src = reinterpret_cast<const float4*>(base + ph * rowpitch + (long long)pw * p.Cin + cc * 8);
+                const float4 lo = src[0], hi = src[1];
+                pk = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+            }
+            *reinterpret_cast<uint4*>(sA + (uint32_t)kc * LBO_P + (uint32_t)r * 16) = pk;
+            if (++cc == cpp) { cc = 0; q++; if (++pw == p.mw) { pw = 0; ph++; } }
+        }
+    } else {
+        for (int kc = 0; kc < nkc; kc++) {
+            float v[8];
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                int k = kc * 8 + e;
-                if (k < p.K) {
-                    int q = k / p.Cin, c = k - q * p.Cin;
-                    int ph = q / p.mw, pw = q - ph * p.mw;
-                    v[e] = in[((b * p.Hf + (Y * p.mh + ph)) * p.Wf + (X * p.mw + pw)) * p.Cin + c];
+                const int k = kc * 8 + e;
+                v[e] = 0.f;
+                if (rowok && k < p.K) {
+                    const int q = k / p.Cin, c = k - q * p.Cin;
+                    const int ph = q / p.mw, pw = q - ph * p.mw;
+                    v[e] = base[ph * rowpitch + (long long)pw * p.Cin + c];
                 }
             }
+            *reinterpret_cast<uint4*>(sA + (uint32_t)kc * LBO_P + (uint32_t)r * 16) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
-        *reinterpret_cast<uint4*>(sA + (uint32_t)kc * LBO_P + (uint32_t)r * 16) =
-            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
 }
 
