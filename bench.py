@@ -264,6 +264,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # ---- attribution pass: per-kernel CUDA-event timing inside the library (eager, same stream) --
         prof = {}
         if rank == 0:
+            ops.set_dual_streams(False)   # one kernel at a time: clean per-kernel durations for the roofline numbers
             ops.profile_enable(True)
             nprof = min(3, args.steps)
             for _ in range(nprof):
@@ -271,6 +272,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             stream.synchronize()
             prof = ops.profile_summary()
             ops.profile_enable(False)
+            ops.set_dual_streams(True)
             for v in prof.values():
                 v["steps"] = nprof
 
@@ -311,6 +313,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
         roofline["avg_launch_us"] = avg_s * 1e6
         roofline["share_of_step"] = tv["total_ms"] / tot if tot else None
+        # the other roof, for reference: algorithmic HBM bytes of the same launches
+        roofline["hbm_gbs_algorithmic"] = tv["bytes"] / tv["launches"] / avg_s / 1e9
+        roofline["hbm_frac_algorithmic"] = roofline["hbm_gbs_algorithmic"] / pk["hbm_gbs"]
+        # measured DRAM traffic per launch of this kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+        # `ncu --set full` capture, committed under profiles/): far above the algorithmic bytes = wasted re-reads
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if top in tj:
+                roofline["traffic"] = tj[top]["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tj[top].get("source")
+                roofline["algorithmic_bytes_per_launch"] = tv["bytes"] / tv["launches"]
 
     cpu = None
     if world == 1 and args.cpu_sample > 0:
@@ -325,7 +340,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "dtype": precision, "data": "synthetic",
             "config": {"workload": f"inference B={B}/GPU {S}x{S} IR+visible pairs, default A000_CONFIG Swin-UNet "
                                    f"(BASELINE configs[1])", "global_batch": B * world, "precision": precision,
-                       "launch": "cuda-graph replay" if graph is not None else "eager",
+                       "launch": ("cuda-graph replay" if graph is not None else "eager") + ", IR / visible paths on two streams",
                        "l2": "per-step activation working set (>2 GB) exceeds the 126 MB L2; no explicit flush",
                        "weights": "synthetic deterministic state_dict (oracle.synth_state_dict)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4,

@@ -3,6 +3,7 @@ self (x<-x, y<-y) vs cross (x: Q=x, KV=y; y: Q=y, KV=x) attention (a002:58-82)."
 from torch import nn
 
 from a001_WindowAttention import WindowAttention
+from swinfuse import ops
 
 
 class AutoPathWinAtt(nn.Module):
@@ -30,12 +31,10 @@ class AutoPathWinAtt(nn.Module):
         if not self.use_dual_path:
             return self.window_attention_x.fused(x, None, ln_q=ln_x, ln_kv=ln_x, residual=x)
         if self.use_cross_att:  # both directions read the pre-update tensors (a002:70-73)
-            ox = self.window_attention_x.fused(x, y, ln_q=ln_x, ln_kv=ln_y, residual=x)
-            oy = self.window_attention_y.fused(y, x, ln_q=ln_y, ln_kv=ln_x, residual=y)
-        else:
-            ox = self.window_attention_x.fused(x, None, ln_q=ln_x, ln_kv=ln_x, residual=x)
-            oy = self.window_attention_y.fused(y, None, ln_q=ln_y, ln_kv=ln_y, residual=y)
-        return ox, oy
+            return ops.dual_path(lambda: self.window_attention_x.fused(x, y, ln_q=ln_x, ln_kv=ln_y, residual=x),
+                                 lambda: self.window_attention_y.fused(y, x, ln_q=ln_y, ln_kv=ln_x, residual=y))
+        return ops.dual_path(lambda: self.window_attention_x.fused(x, None, ln_q=ln_x, ln_kv=ln_x, residual=x),
+                             lambda: self.window_attention_y.fused(y, None, ln_q=ln_y, ln_kv=ln_y, residual=y))
 
     def forward(self, x, y):
         if not self.use_dual_path:

@@ -42,7 +42,7 @@ class AutoPathMLP(nn.Module):
 
     def fused(self, x, y, ln_x, ln_y):
         if self.use_dual_path or y is not None:
-            return self.fused_path("x", x, ln_x, x), self.fused_path("y", y, ln_y, y)
+            return ops.dual_path(lambda: self.fused_path("x", x, ln_x, x), lambda: self.fused_path("y", y, ln_y, y))
         return self.fused_path("x", x, ln_x, x)
 
     def forward(self, x, y):

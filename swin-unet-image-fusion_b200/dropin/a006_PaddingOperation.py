@@ -43,11 +43,14 @@ class MyPadding(nn.Module):
         return ops.crop(tensor, *self.padding_size, add=add)
 
     def do_padding(self, x: Tensor, y: Optional[Tensor]):
-        return self.do_padding_for_one_tensor(x), (None if y is None else self.do_padding_for_one_tensor(y))
+        if y is None:
+            return self.do_padding_for_one_tensor(x), None
+        return ops.dual_path(lambda: self.do_padding_for_one_tensor(x), lambda: self.do_padding_for_one_tensor(y))
 
     def undo_padding(self, x, y, add_x=None, add_y=None):
-        return (self.undo_padding_for_one_tensor(x, add_x),
-                None if y is None else self.undo_padding_for_one_tensor(y, add_y))
+        if y is None:
+            return self.undo_padding_for_one_tensor(x, add_x), None
+        return ops.dual_path(lambda: self.undo_padding_for_one_tensor(x, add_x), lambda: self.undo_padding_for_one_tensor(y, add_y))
 
     def forward(self, x, y, skip=None):
         """``skip`` (decoder only, optional (skip_x, skip_y)): U-Net skip tensors added right after

@@ -53,7 +53,7 @@ class PatchMergingAndLinearLayer(nn.Module):
 
     def forward(self, x, y=None):
         if y is not None:
-            return self._one("x", x), self._one("y", y)
+            return ops.dual_path(lambda: self._one("x", x), lambda: self._one("y", y))
         return self._one("x", x)
 
     def forward_(self, x, y):

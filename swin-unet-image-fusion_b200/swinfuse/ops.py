@@ -84,6 +84,44 @@ def to_nchw_contiguous(x: Tensor) -> Tensor:
     return _NhwcToNchw.apply(x)
 
 
+# ------------------------------------------------------------------------------------------------
+# two-path concurrency
+# ------------------------------------------------------------------------------------------------
+# The IR (x) and visible (y) paths of a block are independent kernel sequences (a002:58-82, a003:46-50;
+# cross attention reads both inputs but writes its own path).  In no-grad mode the y path is issued on a
+# side stream between a fork (side waits for the caller's stream) and a join (the caller's stream waits
+# for the side stream), so the narrow late stages -- whose persistent grids do not fill 148 SMs -- run
+# two kernels at a time.  Every dual operation is fully ordered at both ends, so tensors that cross
+# streams are never reused before their readers were ordered behind the join; the fork/join pattern is
+# also what CUDA-graph capture records as parallel branches.
+_dual_streams = True
+_side_streams = {}
+
+
+def set_dual_streams(on: bool) -> None:
+    global _dual_streams
+    _dual_streams = bool(on)
+
+
+def dual_path(fx, fy):
+    """(fx(), fy()) -- fy on a side stream when gradients are off and both run on a CUDA device."""
+    if not _dual_streams or torch.is_grad_enabled() or not torch.cuda.is_available():
+        return fx(), fy()
+    main = torch.cuda.current_stream()
+    key = main.device.index
+    side = _side_streams.get(key)
+    if side is None:
+        if torch.cuda.is_current_stream_capturing():
+            return fx(), fy()   # a stream cannot be created inside a capture; warm up eagerly first
+        side = _side_streams[key] = torch.cuda.Stream(device=main.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        oy = fy()
+    ox = fx()
+    main.wait_stream(side)
+    return ox, oy
+
+
 _weights_epoch = 0
 
 

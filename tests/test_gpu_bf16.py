@@ -129,6 +129,45 @@ def test_small_model_bf16():
     assert rel_err(out, T(g["out_eval"])) <= TOL_BF16
 
 
+def test_two_stream_paths_and_graph_replay_are_bit_identical():
+    """The IR / visible paths run on two streams (ops.dual_path) and the bench replays a CUDA graph of
+    that: both must reproduce the single-stream eager result bit for bit (kernels are deterministic)."""
+    sw = dropin()
+    m = build_model().eval()
+    m.load_state_dict(fo.synth_state_dict(), strict=True)
+    ir, vis = fo.synth_inputs(4, 256, 256)
+    ir, vis = ir.cuda(), vis.cuda()
+    with torch.no_grad():
+        sw.ops.set_dual_streams(False)
+        ref = m(ir, vis).clone()
+        sw.ops.set_dual_streams(True)
+        for _ in range(3):
+            two = m(ir, vis)
+            assert torch.equal(two, ref)
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(graph, stream=stream):
+                gout = m(ir, vis)
+            for _ in range(3):
+                graph.replay()
+                stream.synchronize()
+                assert torch.equal(gout, ref)
+            # new inputs through the same graph
+            ir2, vis2 = fo.synth_inputs(4, 256, 256, seed=11)
+            ir.copy_(ir2.cuda()); vis.copy_(vis2.cuda())
+            graph.replay()
+            stream.synchronize()
+            got2 = gout.clone()
+        torch.cuda.current_stream().wait_stream(stream)
+        sw.ops.set_dual_streams(False)
+        ref2 = m(ir, vis)
+        sw.ops.set_dual_streams(True)
+        assert torch.equal(got2, ref2)
+
+
 def test_unsupported_shapes_raise_not_fallback():
     sw = dropin()
     x = torch.randn(1, 6, 7, 7, device="cuda")  # C % 4 != 0
