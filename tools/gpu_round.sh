@@ -17,11 +17,13 @@ if [ "$2" = "full" ]; then
   cat $out/${tag}_reference_arm.json | cut -c1-400
 fi
 # launch list of the same command (serialised, cold-cache: shares only)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $out/${tag}_ncu_launches.csv \
-    python bench.py --steps 1 --warmup 1 --no-graph --cpu-sample 0 > $out/${tag}_ncu_bench.log 2>&1
+# (capped at the first 3000 launches = the eager warm-up forwards plus the start of the graph replays: ncu serialises and
+#  replays every launch, the whole default run would take tens of minutes of box time)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_ncu_launches.csv \
+    python bench.py --steps 2 --warmup 1 --cpu-sample 0 > $out/${tag}_ncu_bench.log 2>&1
 python tools/ncu_launch_summary.py $out/${tag}_ncu_launches.csv > $out/${tag}_ncu_launch_summary.txt 2>&1; head -30 $out/${tag}_ncu_launch_summary.txt
 # full capture of the dominant kernel on its own (stage-0 window attention, B=64)
-K=${NCU_KERNEL:-k_attn_mma}
+K=${NCU_KERNEL:-k_attn_pack4}
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K" -s 1 -c 1 -o $out/${tag}_full_top \
     python tools/prof_ops.py wa 0 shift > $out/${tag}_ncu_full.log 2>&1
 ncu -i $out/${tag}_full_top.ncu-rep --page raw --csv > $out/${tag}_full_top_raw.csv 2>/dev/null
