@@ -93,6 +93,7 @@ struct TcMlp {
     const bf16* W2p;   // UMMA image [Hpad/8][Cpad][8]   (rows = output channel, k = hidden unit)
     const float* b1;   // [Hpad] zero padded
     const float* b2;   // [Cpad] zero padded
+    int max_stages;    // depth cap of the raw-tile ring (<= 8)
 };
 bool tc_mlp_supported(int C, int hidden);
 int launch_tc_mlp(const TcMlp& t, cudaStream_t st);

@@ -3,6 +3,7 @@
 // how the caller's workspace is carved.  Every linear layer goes through tcgen05.mma (tc_gemm.cu);
 // the per-window attention core runs on HMMA tiles (attn_frag.cu); LayerNorm, softmax, bias, ELU and
 // the residual stream stay fp32.
+#include <cstdlib>
 #include "bf16_kernels.cuh"
 #include "fp32_kernels.cuh"
 #include "tc_common.cuh"
@@ -265,6 +266,8 @@ int mlp_fwd_bf16(const sf_mlp_params* p, void* ws_ptr, size_t ws_bytes, cudaStre
         t.x = p->in; t.residual = p->residual; t.out = p->out; t.M = p->M;
         t.C = p->C; t.Cpad = m.g1.kpad; t.hidden = p->hidden; t.Hpad = m.g1.nch;
         t.ln_g = p->ln_gamma; t.ln_b = p->ln_beta; t.eps = p->ln_eps;
+        t.max_stages = 8;
+        if (const char* e = getenv("SWINFUSE_MLP_STAGES")) t.max_stages = atoi(e) < 2 ? 2 : (atoi(e) > 8 ? 8 : atoi(e));
         t.W1p = reinterpret_cast<const bf16*>(pk + m.g1.off_w); t.b1 = reinterpret_cast<const float*>(pk + m.g1.off_b);
         t.W2p = reinterpret_cast<const bf16*>(pk + m.g2.off_w); t.b2 = reinterpret_cast<const float*>(pk + m.g2.off_b);
         if (m.g2.nch != t.Cpad || m.g2.kpad != t.Hpad) { set_error("mlp: packed weight plan does not match the fused kernel"); return SF_ERR_INVALID; }

@@ -38,7 +38,7 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
 }
 
 struct MlpSmem { uint32_t w1, w2, a1[2], a2[2], b1, b2, bars, ring, tile_bytes, nstage, total; };
-__host__ __device__ static inline MlpSmem mlp_smem_layout(int Kpad, int Hpad, int N2, int C) {
+__host__ __device__ static inline MlpSmem mlp_smem_layout(int Kpad, int Hpad, int N2, int C, int max_stages = M_MAX_STAGES) {
     MlpSmem s{};
     uint32_t o = 0;
     s.w1 = o; o += al128((uint32_t)Hpad * Kpad * 2);
@@ -52,7 +52,7 @@ __host__ __device__ static inline MlpSmem mlp_smem_layout(int Kpad, int Hpad, in
     s.tile_bytes = al128(128u * (uint32_t)C * 4u);
     const uint32_t room = o < (uint32_t)M_SMEM_LIMIT ? (uint32_t)M_SMEM_LIMIT - o : 0u;
     s.nstage = room / s.tile_bytes;
-    if (s.nstage > (uint32_t)M_MAX_STAGES) s.nstage = M_MAX_STAGES;
+    if (s.nstage > (uint32_t)max_stages) s.nstage = max_stages;
     s.total = o + s.nstage * s.tile_bytes;
     return s;
 }
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Kpad = p.Cpad, Hpad = p.Hpad, N2 = p.Cpad;
-    const MlpSmem L = mlp_smem_layout(Kpad, Hpad, N2, p.C);
+    const MlpSmem L = mlp_smem_layout(Kpad, Hpad, N2, p.C, p.max_stages);
     const uint32_t NS = L.nstage;
     // the residual is x itself (a003 through a004:29-38) and the ring is deep enough: take it from the ring
     const bool ring_res = p.residual == p.x && NS >= (uint32_t)M_RES_MIN_STAGES;
@@ -172,12 +172,15 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
                 float4 v[NF];
                 mbar_wait_relaxed(&x_full[st], sp);
                 mlp_load_row<NF>(v, smem + L.ring + st * L.tile_bytes, r, tile * 128 + r < p.M, p.C);
-                mbar_arrive1(&x_empty[st]);   // (with ring_res the output stage holds the slot a little longer)
                 const uint32_t b = (uint32_t)t & 1u;
                 mbar_wait_relaxed(&a1_empty[b], (((uint32_t)t >> 1) & 1u) ^ 1u);
                 mlp_finish_row<NF>(smem + L.a1[b], v, r, p.C, Kpad, p.ln_g, p.ln_b, p.eps);
                 fence_async_smem();
                 mbar_arrive1(&a1_full[b]);
+                // release the ring slot only now: the row has been consumed, so its ld.shared have returned
+                // (an arrive issued right behind the loads can let the loader's bulk copy overwrite the slot
+                // while they are still in flight -- observed as a data race at C = 48)
+                mbar_arrive1(&x_empty[st]);
             }
         };
         if (Kpad <= 32) run(std::integral_constant<int, 8>{});
@@ -283,8 +286,6 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
                 const float4* rs = reinterpret_cast<const float4*>(smem + L.ring + st * L.tile_bytes + (size_t)row * p.C * 4);
 #pragma unroll
                 for (int i = 0; i < 16; i++) rr[i] = (rowok && i < nf4) ? rs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncwarp();
-                if (lane == 0) mbar_arrive1(&x_empty[st]);
             } else if (p.residual) {
                 const float4* rs = reinterpret_cast<const float4*>(p.residual + m * p.C);
 #pragma unroll
@@ -319,7 +320,10 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive1(&d2_empty[b]);
+            if (lane == 0) {
+                mbar_arrive1(&d2_empty[b]);
+                if (ring_res) mbar_arrive1(&x_empty[(uint32_t)(t % NS)]);   // residual consumed (stores issued): slot free
+            }
         }
     }
     tc_fence_before_sync();
@@ -338,7 +342,7 @@ bool tc_mlp_supported(int C, int hidden) {
 
 int launch_tc_mlp(const TcMlp& t, cudaStream_t st) {
     SF_CHECK_ARG(tc_mlp_supported(t.C, t.hidden), "tc_mlp: unsupported shape C=%d hidden=%d", t.C, t.hidden);
-    const MlpSmem L = mlp_smem_layout(t.Cpad, t.Hpad, t.Cpad, t.C);
+    const MlpSmem L = mlp_smem_layout(t.Cpad, t.Hpad, t.Cpad, t.C, t.max_stages);
     static thread_local bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM_LIMIT);
