@@ -152,7 +152,7 @@ def run_reference(args, rank: int):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,7 +347,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_fwd * args.steps,
             "model_tflops": model_tf, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_train(args, rank: int, world: int, local_rank: int):
@@ -418,10 +418,29 @@ def run_train(args, rank: int, world: int, local_rank: int):
                        "launch": "eager"},
             "gpu_launches": launches * args.steps, "loss_first": float(loss0), "loss_last": float(loss), "clocks": clocks,
             "model_tflops": pairs / (ms / 1e3) * 3 * GFLOP_PER_PAIR_256 * (S / 256.0) ** 2 / 1e3, "kernels": kernels}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    # Libraries (NCCL's version banner, for one) write to fd 1: keep the real stdout for the JSON line only and
+    # send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.batch is None:
         args.batch = 64 if args.mode == "infer" else 32
