@@ -362,7 +362,7 @@ def run_train(args, rank: int, world: int, local_rank: int):
     from swinfuse.loss_ops import FusionLoss
     from swinfuse.train import DataParallelTrainer
     loss_fn = FusionLoss().to(dev)
-    trainer = DataParallelTrainer(model, loss_fn, lr=1e-2)
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-2, use_graph=not args.no_graph)
     B, S = args.batch, args.size
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)
     ir = torch.rand(B, 1, S, S, generator=g).to(dev)
@@ -377,7 +377,7 @@ def run_train(args, rank: int, world: int, local_rank: int):
     ops.reset_launch_count()
     loss0 = trainer.step(ir, vis)
     launches = ops.launch_count()
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(max(2, args.warmup - 1)):   # the third step captures the CUDA graph of forward + loss + backward
         trainer.step(ir, vis)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -393,7 +393,8 @@ def run_train(args, rank: int, world: int, local_rank: int):
     prof = {}
     if rank == 0:
         ops.profile_enable(True)
-    trainer.step(ir, vis)   # attribution pass: every rank steps (the step contains the gradient all-reduce)
+    trainer.use_graph = False   # attribution pass runs eagerly (CUDA-event brackets around every launch)
+    trainer.step(ir, vis)   # every rank steps (the step contains the gradient all-reduce)
     torch.cuda.synchronize()
     if rank == 0:
         prof = ops.profile_summary()
@@ -415,7 +416,7 @@ def run_train(args, rank: int, world: int, local_rank: int):
                        "global_batch": B * world, "loss": "a008 semantics via swinfuse.loss_ops (torch ops, parity unpinned)",
                        "optimizer": "Adam lr 1e-2, sf_adam_step over one flat buffer",
                        "collective": "one NCCL all-reduce of the flat fp32 gradient buffer" if world > 1 else "none",
-                       "launch": "eager"},
+                       "launch": "eager" if args.no_graph else "cuda-graph replay of zero-grad + forward + loss + backward; all-reduce + Adam eager"},
             "gpu_launches": launches * args.steps, "loss_first": float(loss0), "loss_last": float(loss), "clocks": clocks,
             "model_tflops": pairs / (ms / 1e3) * 3 * GFLOP_PER_PAIR_256 * (S / 256.0) ** 2 / 1e3, "kernels": kernels}
     emit(line)

@@ -92,20 +92,57 @@ class FlatAdam:
 
 
 class DataParallelTrainer:
-    """forward -> clamp (a016:153) -> loss -> backward -> gradient all-reduce -> Adam, per rank."""
+    """forward -> clamp (a016:153) -> loss -> backward -> gradient all-reduce -> Adam, per rank.
 
-    def __init__(self, model: torch.nn.Module, loss_fn, lr: float = 1e-2, group=None, n_buckets: int = 1):
+    ``use_graph``: after two eager warm-up steps the device work of zero-grad + forward + loss + backward
+    (about 10k kernel launches) is captured once into a CUDA graph and replayed on static input buffers;
+    the gradient all-reduce and the Adam kernel (whose bias correction depends on the step count) stay eager.
+    Shapes must then stay fixed; a new shape re-captures."""
+
+    def __init__(self, model: torch.nn.Module, loss_fn, lr: float = 1e-2, group=None, n_buckets: int = 1,
+                 use_graph: bool = False):
         self.model, self.loss_fn, self.group, self.n_buckets = model, loss_fn, group, n_buckets
         self.flat = FlatParameters(model.parameters())
         self.opt = FlatAdam(self.flat, lr=lr)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graph = use_graph
+        self._graph, self._shape, self._eager_steps = None, None, 0
 
-    def step(self, ir: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
+    def _forward_backward(self, ir: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
         self.flat.zero_grad()
         fusion = self.model(ir, vis)
         fusion = torch.clamp(fusion, 0, 1)
         loss = self.loss_fn(fusion, ir, vis)
         loss.backward()
+        return loss.detach()
+
+    def _capture(self, ir: torch.Tensor, vis: torch.Tensor) -> None:
+        self._ir, self._vis = ir.clone(), vis.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # autograd's stream bookkeeping wants a warm-up on the capturing side stream
+            self._forward_backward(self._ir, self._vis)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        # the autograd engine runs backward nodes (and their allocations) on its own thread: thread-local capture mode
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+            self._loss = self._forward_backward(self._ir, self._vis)
+        self._shape = (tuple(ir.shape), tuple(vis.shape))
+
+    def step(self, ir: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
+        if self.use_graph and ir.is_cuda:
+            if self._eager_steps < 2:      # first-call checks, packed-weight buffers, cuDNN plans
+                self._eager_steps += 1
+                loss = self._forward_backward(ir, vis)
+            else:
+                if self._graph is None or self._shape != (tuple(ir.shape), tuple(vis.shape)):
+                    self._capture(ir, vis)
+                self._ir.copy_(ir)
+                self._vis.copy_(vis)
+                self._graph.replay()
+                loss = self._loss
+        else:
+            loss = self._forward_backward(ir, vis)
         self.flat.all_reduce_grads(self.group, self.n_buckets)
         self.opt.step(grad_scale=1.0 / self.world)
-        return loss.detach()
+        return loss
