@@ -347,6 +347,115 @@ __global__ void k_attn_core_bwd(const float* __restrict__ Q, const float* __rest
         for (int i = threadIdx.x; i < tabn; i += blockDim.x) atomicAdd(&gtable[i], tacc[i]);
 }
 
+// 7x7 windows (the model's only window size): the same algorithm with compile-time window constants --
+// no integer divisions in the inner loops, unrolled key loops, and the gradient of the 13x13 bias table
+// accumulated in registers (each query row owns 49 distinct table entries) instead of 2401 shared-memory
+// atomics per (window, head); one global atomicAdd per entry and thread at the end of the kernel.
+__global__ void __launch_bounds__(64) k_attn_core_bwd_w7(const float* __restrict__ Q, const float* __restrict__ Kt, const float* __restrict__ V,
+                                                       const float* __restrict__ gO, float* __restrict__ dQ, float* __restrict__ dK,
+                                                       float* __restrict__ dV, const float* __restrict__ table, float* __restrict__ gtable,
+                                                       WinGeom g, int inner, int nh, int d, float scale, long long nitems) {
+    constexpr int T = 49, TS = 51, TW = 13;   // TS odd: row-strided accesses of a warp are conflict-free
+    extern __shared__ float smb[];
+    float* Qs = smb;                    // [T][d]
+    float* Ks = Qs + T * d;
+    float* Vs = Ks + T * d;
+    float* Gs = Vs + T * d;             // dO
+    float* Ps = Gs + T * d;             // [T][TS]
+    float* Ss = Ps + T * TS;            // dS [T][TS]
+    float* tab = Ss + T * TS;           // [169]
+    long long* rows = reinterpret_cast<long long*>(tab + 169 + ((169 + 4 * T * d + 2 * T * TS) & 1));
+    int* regs = reinterpret_cast<int*>(rows + T);
+    for (int i = threadIdx.x; i < 169; i += blockDim.x) tab[i] = table[i];
+    const int qi = threadIdx.x;
+    const bool active = qi < T;
+    const int qr = qi / 7, qc = qi - qr * 7;
+    const int qoff = (6 - qr) * TW + (6 - qc);   // table index of (query qi, key j) = qoff + (j/7)*13 + j%7
+    float tl[T];                                  // this query row's 49 table-gradient entries
+#pragma unroll
+    for (int j = 0; j < T; j++) tl[j] = 0.f;
+
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int win = (int)(item / nh), head = (int)(item % nh);
+        __syncthreads();
+        if (active) {
+            int rg;
+            rows[qi] = win_token_src(g, win, qi, &rg);
+            regs[qi] = rg;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * d; i += blockDim.x) {
+            int t = i / d, dd = i - t * d;
+            long long off = rows[t] * inner + head * d + dd;
+            Qs[i] = Q[off]; Ks[i] = Kt[off]; Vs[i] = V[off]; Gs[i] = gO[off];
+        }
+        __syncthreads();
+        if (active) {
+            const int qreg = regs[qi];
+            float* Pr = Ps + qi * TS;
+            float* Sr = Ss + qi * TS;
+            float mx = -INFINITY;
+#pragma unroll 7
+            for (int j = 0; j < T; j++) {
+                float s = 0.f, dp = 0.f;
+                for (int dd = 0; dd < d; dd++) {
+                    s = fmaf(Qs[qi * d + dd], Ks[j * d + dd], s);
+                    dp = fmaf(Gs[qi * d + dd], Vs[j * d + dd], dp);
+                }
+                s = s * scale + tab[qoff + (j / 7) * TW + (j % 7)];
+                if (regs[j] != qreg) s = -1e10f;
+                Pr[j] = s;
+                Sr[j] = dp;
+                mx = fmaxf(mx, s);
+            }
+            float sum = 0.f;
+#pragma unroll 7
+            for (int j = 0; j < T; j++) { float e = expf(Pr[j] - mx); Pr[j] = e; sum += e; }
+            const float inv = 1.f / sum;
+            float delta = 0.f;
+#pragma unroll 7
+            for (int j = 0; j < T; j++) {
+                float p = Pr[j] * inv;
+                Pr[j] = p;
+                delta = fmaf(p, Sr[j], delta);
+            }
+#pragma unroll
+            for (int j = 0; j < T; j++) {
+                const float ds = Pr[j] * (Sr[j] - delta);
+                Sr[j] = ds;
+                tl[j] += ds;
+            }
+            const long long off = rows[qi] * inner + head * d;
+            for (int dd = 0; dd < d; dd++) {
+                float a = 0.f;
+#pragma unroll 7
+                for (int j = 0; j < T; j++) a = fmaf(Sr[j], Ks[j * d + dd], a);
+                dQ[off + dd] = a * scale;
+            }
+        }
+        __syncthreads();
+        if (active) {
+            const int kj = qi;
+            const long long off = rows[kj] * inner + head * d;
+            for (int dd = 0; dd < d; dd++) {
+                float a = 0.f, b = 0.f;
+#pragma unroll 7
+                for (int i = 0; i < T; i++) {
+                    a = fmaf(Ss[i * TS + kj], Qs[i * d + dd], a);
+                    b = fmaf(Ps[i * TS + kj], Gs[i * d + dd], b);
+                }
+                dK[off + dd] = a * scale;
+                dV[off + dd] = b;
+            }
+        }
+    }
+    if (gtable && active) {
+#pragma unroll
+        for (int j = 0; j < T; j++)
+            if (tl[j] != 0.f) atomicAdd(&gtable[qoff + (j / 7) * TW + (j % 7)], tl[j]);
+    }
+}
+
 static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
                                 const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st) {
     const int tabn = (2 * g.wsh - 1) * (2 * g.wsw - 1);
@@ -367,6 +476,23 @@ static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, 
     if (grid > nitems) grid = nitems;
     const double mtok = (double)g.B * g.Hp * g.Wp;
     ProfScope ps("bwd_attn_core_f32", 12.0 * g.T * mtok * inner, 28.0 * mtok * inner, st);
+    if (g.wsh == 7 && g.wsw == 7) {
+        const size_t smem7 = ((size_t)4 * 49 * d + 2 * 49 * 51 + 169 + 2) * sizeof(float) + 49 * 12 + 16;
+        static thread_local bool configured7 = false;
+        if (!configured7) {
+            cudaError_t e = cudaFuncSetAttribute(k_attn_core_bwd_w7, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) { set_error("attention backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
+            configured7 = true;
+        }
+        int psm = (int)((200 * 1024) / (smem7 + 1024));
+        if (psm > 16) psm = 16;
+        if (psm < 1) psm = 1;
+        long long grid7 = 148LL * psm;
+        if (grid7 > nitems) grid7 = nitems;
+        k_attn_core_bwd_w7<<<(unsigned)grid7, 64, smem7, st>>>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, d, 1.0f / sqrtf((float)d), nitems);
+        SF_CHECK_LAUNCH("bwd_attn_core");
+        return SF_OK;
+    }
     k_attn_core_bwd<<<(unsigned)grid, threads, smem, st>>>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, d, 1.0f / sqrtf((float)d), nitems);
     SF_CHECK_LAUNCH("bwd_attn_core");
     return SF_OK;
