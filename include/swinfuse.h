@@ -77,6 +77,15 @@ int sf_profile_summary(sf_profile_entry* out, int max_entries);
 int sf_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, void* stream);
 int sf_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, void* stream);
 
+/* Inference edges of a017_test.py, batched on the device.
+ * sf_bgr_to_ycrcb: a015_dataset.py:86-93 (cv2.cvtColor(vis, COLOR_BGR2YCrCb) on uint8, OpenCV's 14-bit fixed point,
+ *   bit-exact) + a015:56-60 (v2.ToImage, v2.ToDtype(float32, scale=True): u8 * fl32(1/255)) + the split of
+ *   a017:68.  bgr (B,H,W,3) uint8 -> y (B,1,H,W), crcb (B,2,H,W) fp32.
+ * sf_ycrcb_to_rgb: a017:83-88 (clamp_(fus_y,0,1); concat with CrCb; cv2.cvtColor(float32, COLOR_YCrCb2RGB)).
+ *   fus_y (B,1,H,W), crcb (B,2,H,W) -> rgb (B,3,H,W) fp32, bit-exact with OpenCV's fused-multiply-add path. */
+int sf_bgr_to_ycrcb(const uint8_t* bgr, float* y, float* crcb, int B, int H, int W, void* stream);
+int sf_ycrcb_to_rgb(const float* fus_y, const float* crcb, float* rgb, int B, int H, int W, void* stream);
+
 /* MyPadding encoder branch, a006:111-131: reflect pad bottom/right.
  * in (B,H,W,C) -> out (B,H+pad_down,W+pad_right,C); out[L+k] = in[L-2-k]; needs pad < L. */
 int sf_pad_reflect(const float* in, float* out, int B, int H, int W, int C, int pad_down, int pad_right,

@@ -86,6 +86,8 @@ SIGNATURES = {
     "sf_profile_summary": (_i, [C.POINTER(ProfileEntry), _i]),
     "sf_nchw_to_nhwc": (_i, [_f, _f, _i, _i, _i, _i, _f]),
     "sf_nhwc_to_nchw": (_i, [_f, _f, _i, _i, _i, _i, _f]),
+    "sf_bgr_to_ycrcb": (_i, [_f, _f, _f, _i, _i, _i, _f]),
+    "sf_ycrcb_to_rgb": (_i, [_f, _f, _f, _i, _i, _i, _f]),
     "sf_pad_reflect": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "sf_pad_reflect_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "sf_crop": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),

@@ -85,6 +85,37 @@ def to_nchw_contiguous(x: Tensor) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# inference edges of a017_test.py
+# ------------------------------------------------------------------------------------------------
+def bgr_to_y_crcb(bgr: Tensor) -> Tuple[Tensor, Tensor]:
+    """(B,H,W,3) uint8 BGR on the device -> (y (B,1,H,W), crcb (B,2,H,W)) float32: cv2 BGR2YCrCb on uint8 +
+    ToImage/ToDtype(scale=True) + the split of a017:68, bit-exact (a015:86-93, a015:56-60)."""
+    if not isinstance(bgr, torch.Tensor) or not bgr.is_cuda:
+        raise SwinFuseError("bgr_to_y_crcb: expected a CUDA tensor (libswinfuse has no CPU path)")
+    if bgr.dtype != torch.uint8 or bgr.dim() != 4 or bgr.shape[-1] != 3:
+        raise SwinFuseError(f"bgr_to_y_crcb expects a (B,H,W,3) uint8 tensor, got {tuple(bgr.shape)} {bgr.dtype}")
+    bgr = bgr.contiguous()
+    b, h, w, _ = bgr.shape
+    y = torch.empty((b, 1, h, w), dtype=torch.float32, device=bgr.device)
+    crcb = torch.empty((b, 2, h, w), dtype=torch.float32, device=bgr.device)
+    check(_lib.load().sf_bgr_to_ycrcb(bgr.data_ptr(), y.data_ptr(), crcb.data_ptr(), b, h, w, _stream()), "sf_bgr_to_ycrcb")
+    return y, crcb
+
+
+def y_crcb_to_rgb(fus_y: Tensor, crcb: Tensor) -> Tensor:
+    """clamp(fus_y,0,1), re-attach CrCb, YCrCb -> RGB as cv2 does on float32 (a017:83-88); (B,3,H,W) float32."""
+    _require_cuda(fus_y, "fus_y")
+    _require_cuda(crcb, "crcb")
+    b, c, h, w = fus_y.shape
+    if c != 1 or tuple(crcb.shape) != (b, 2, h, w) or fus_y.dtype != torch.float32 or crcb.dtype != torch.float32:
+        raise SwinFuseError(f"y_crcb_to_rgb expects fus_y (B,1,H,W) and crcb (B,2,H,W) float32, got {tuple(fus_y.shape)}, {tuple(crcb.shape)}")
+    fus_y, crcb = fus_y.contiguous(), crcb.contiguous()
+    rgb = torch.empty((b, 3, h, w), dtype=torch.float32, device=fus_y.device)
+    check(_lib.load().sf_ycrcb_to_rgb(fus_y.data_ptr(), crcb.data_ptr(), rgb.data_ptr(), b, h, w, _stream()), "sf_ycrcb_to_rgb")
+    return rgb
+
+
+# ------------------------------------------------------------------------------------------------
 # two-path concurrency
 # ------------------------------------------------------------------------------------------------
 # The IR (x) and visible (y) paths of a block are independent kernel sequences (a002:58-82, a003:46-50;
