@@ -81,6 +81,21 @@ def test_bf16_batch_64_equals_per_sample_runs():
     assert rel_err(full[17:18], ref) <= TOL_BF16
 
 
+def test_high_res_1024_bf16_padding_and_mask_paths():
+    """BASELINE config 4 on the tensor-core path: 1024x1024 (pad 6 at stage 0, pad 1 at stages 2-3, 5,476-window
+    shift masks, 21,904 windows per stage-0 launch) against the CPU oracle, and B=2 equal to per-sample runs."""
+    m = build_model().eval()
+    sd = fo.synth_state_dict()
+    m.load_state_dict(sd, strict=True)
+    ir, vis = fo.synth_inputs(2, 1024, 1024, seed=9)
+    with torch.no_grad():
+        out = m(ir.cuda(), vis.cuda())
+        one = m(ir[1:2].cuda(), vis[1:2].cuda())
+        ref = fo.model_forward(sd, ir[1:2], vis[1:2])
+    assert torch.equal(one[0], out[1])
+    assert rel_err(out[1:2], ref) <= TOL_BF16, rel_err(out[1:2], ref)
+
+
 def test_window_attention_golden_cases_bf16():
     dropin()
     from a001_WindowAttention import WindowAttention
