@@ -13,6 +13,125 @@ namespace sf {
 __device__ __forceinline__ float elu_grad(float pre) { return pre > 0.f ? 1.f : expf(pre); }
 
 // =============================================================================================
+// TF32 tensor-core variants of the two backward GEMMs (used when the operator runs in SF_PREC_BF16:
+// the forward pass is bf16 there, so 10-bit-mantissa products with fp32 accumulation are well inside
+// its tolerance; SF_PREC_FP32 keeps the exact FFMA kernels below).  Same 64x64x16 tiling and the same
+// shared-memory layout [reduction index][m or n] for both operands, so one fragment routine serves
+// dX = dY W and dW = dY^T X:  8 warps, warp w -> rows 16*(w%4), columns 32*(w/4) (4 n-tiles of 8),
+// mma.sync.m16n8k8.tf32, operands rounded to tf32 (cvt.rna) when they are written to shared memory.
+// =============================================================================================
+static constexpr int TS_LD = 64 + 8;   // row pitch: 72 % 32 == 8 -> the (tq, gq) fragment reads hit 32 distinct banks
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// acc[nt][*] += P^T Q for one 16-deep slice: P = Ps[16][TS_LD] (this warp's 16 columns at mrow), Q = Qs[16][TS_LD]
+__device__ __forceinline__ void tile_mma_tf32(const float (*Ps)[TS_LD], const float (*Qs)[TS_LD], int mrow, int ncol, int gq, int tq,
+                                              float (&acc)[4][4]) {
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 8) {
+        const uint32_t a0 = __float_as_uint(Ps[kk + tq][mrow + gq]), a1 = __float_as_uint(Ps[kk + tq][mrow + gq + 8]);
+        const uint32_t a2 = __float_as_uint(Ps[kk + tq + 4][mrow + gq]), a3 = __float_as_uint(Ps[kk + tq + 4][mrow + gq + 8]);
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const uint32_t b0 = __float_as_uint(Qs[kk + tq][ncol + nt * 8 + gq]), b1 = __float_as_uint(Qs[kk + tq + 4][ncol + nt * 8 + gq]);
+            mma_tf32(acc[nt], a0, a1, a2, a3, b0, b1);
+        }
+    }
+}
+
+template <bool ACCUM, bool ELUAUX>
+__global__ void __launch_bounds__(256) k_gemm_nn_tf32(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ aux,
+                                                      float* __restrict__ C, long long M, int N, int K) {
+    __shared__ __align__(16) float As[16][TS_LD];
+    __shared__ __align__(16) float Bs[16][TS_LD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    const int mrow = (warp & 3) * 16, ncol = (warp >> 2) * 32;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        {
+            const int lrow = tid >> 2, lk = (tid & 3) * 4;
+            const long long m = m0 + lrow;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int k = k0 + lk + e;
+                As[lk + e][lrow] = (m < M && k < K) ? to_tf32(A[m * K + k]) : 0.f;
+            }
+        }
+        {
+            const int lk = tid >> 4, ln = (tid & 15) * 4;
+            const int k = k0 + lk;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int n = n0 + ln + e;
+                Bs[lk][ln + e] = (k < K && n < N) ? to_tf32(B[(long long)k * N + n]) : 0.f;
+            }
+        }
+        __syncthreads();
+        tile_mma_tf32(As, Bs, mrow, ncol, gq, tq, acc);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const long long m = m0 + mrow + gq + (e >> 1) * 8;
+            const int n = n0 + ncol + nt * 8 + 2 * tq + (e & 1);
+            if (m >= M || n >= N) continue;
+            float v = acc[nt][e];
+            if (ELUAUX) v *= elu_grad(aux[m * N + n]);
+            if (ACCUM) v += C[m * N + n];
+            C[m * N + n] = v;
+        }
+    }
+}
+
+template <bool ELU_A>
+__global__ void __launch_bounds__(256) k_gemm_tn_reduce_tf32(const float* __restrict__ G, const float* __restrict__ A, float* __restrict__ Wg,
+                                                             long long M, int N, int K, long long rows_per_split) {
+    __shared__ __align__(16) float Gs[16][TS_LD];
+    __shared__ __align__(16) float As[16][TS_LD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const long long r0 = (long long)blockIdx.z * rows_per_split;
+    const long long r1 = min(M, r0 + rows_per_split);
+    const int mrow = (warp & 3) * 16, ncol = (warp >> 2) * 32;
+    float acc[4][4] = {};
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    for (long long r = r0; r < r1; r += 16) {
+        const long long m = r + lr;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            int n = n0 + lc + e, k = k0 + lc + e;
+            Gs[lr][lc + e] = (m < r1 && n < N) ? to_tf32(G[m * N + n]) : 0.f;
+            float a = (m < r1 && k < K) ? A[m * K + k] : 0.f;
+            As[lr][lc + e] = to_tf32(ELU_A ? elu1(a) : a);
+        }
+        __syncthreads();
+        tile_mma_tf32(Gs, As, mrow, ncol, gq, tq, acc);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int n = n0 + mrow + gq + (e >> 1) * 8;
+            const int k = k0 + ncol + nt * 8 + 2 * tq + (e & 1);
+            if (n < N && k < K) atomicAdd(&Wg[(long long)n * K + k], acc[nt][e]);
+        }
+    }
+}
+
+// =============================================================================================
 // C[M,N] (+)= (A[M,K] * B[K,N]) (* ELU'(aux[M,N]))          B row-major [K][N]
 // =============================================================================================
 template <bool ACCUM, bool ELUAUX>
@@ -73,9 +192,21 @@ __global__ void __launch_bounds__(256) k_gemm_nn(const float* __restrict__ A, co
 }
 
 static int launch_gemm_nn(const float* A, const float* B, const float* aux, float* C, long long M, int N, int K, bool accum,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool tf32 = false) {
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
-    ProfScope ps("bwd_gemm_nn_f32", 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)M * N * (accum ? 2 : 1) + (double)K * N), st);
+    ProfScope ps(tf32 ? "bwd_gemm_nn_tf32" : "bwd_gemm_nn_f32", 2.0 * (double)M * N * K,
+                 4.0 * ((double)M * K + (double)M * N * (accum ? 2 : 1) + (double)K * N), st);
+    if (tf32) {
+        if (aux) {
+            if (accum) k_gemm_nn_tf32<true, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+            else k_gemm_nn_tf32<false, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+        } else {
+            if (accum) k_gemm_nn_tf32<true, false><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+            else k_gemm_nn_tf32<false, false><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
+        }
+        SF_CHECK_LAUNCH("bwd_gemm_nn");
+        return SF_OK;
+    }
     if (aux) {
         if (accum) k_gemm_nn<true, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
         else k_gemm_nn<false, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
@@ -135,7 +266,8 @@ __global__ void __launch_bounds__(256) k_gemm_tn_reduce(const float* __restrict_
     }
 }
 
-static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long long M, int N, int K, bool elu_a, cudaStream_t st) {
+static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long long M, int N, int K, bool elu_a, cudaStream_t st,
+                                 bool tf32 = false) {
     if (!Wg) return SF_OK;
     const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
     long long splits = (148LL * 4 + tiles - 1) / tiles;
@@ -146,8 +278,11 @@ static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long
     long long rps = ((M + splits - 1) / splits + 15) / 16 * 16;
     splits = (M + rps - 1) / rps;
     dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + 63) / 64), (unsigned)splits);
-    ProfScope ps("bwd_gemm_wgrad_f32", 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)M * N), st);
-    if (elu_a) k_gemm_tn_reduce<true><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
+    ProfScope ps(tf32 ? "bwd_gemm_wgrad_tf32" : "bwd_gemm_wgrad_f32", 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)M * N), st);
+    if (tf32) {
+        if (elu_a) k_gemm_tn_reduce_tf32<true><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
+        else k_gemm_tn_reduce_tf32<false><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
+    } else if (elu_a) k_gemm_tn_reduce<true><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
     else k_gemm_tn_reduce<false><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
     SF_CHECK_LAUNCH("bwd_gemm_wgrad");
     return SF_OK;
@@ -516,6 +651,7 @@ size_t window_attn_bwd_ws(const sf_window_attn_bwd_params* bp) {
 }
 
 int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: TF32 tensor-core GEMMs in the backward pass
     const sf_window_attn_params* p = &bp->fwd;
     const long long M = (long long)p->B * p->Hp * p->Wp;
     const int C = p->C, inner = p->num_heads * p->head_dim;
@@ -552,28 +688,28 @@ int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws
     SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
     // ---- output projection ----------------------------------------------------------------------------
     SF_TRY(launch_colsum(bp->gout, bp->g_bo, M, C, st));
-    SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st));
-    SF_TRY(launch_gemm_nn(bp->gout, p->wo, nullptr, gO, M, inner, C, false, st));
+    SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st, tf));
+    SF_TRY(launch_gemm_nn(bp->gout, p->wo, nullptr, gO, M, inner, C, false, st, tf));
     // ---- attention core ---------------------------------------------------------------------------------
     SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st));
     // ---- projections --------------------------------------------------------------------------------------
     SF_TRY(launch_colsum(dQ, bp->g_bq, M, inner, st));
     SF_TRY(launch_colsum(dK, bp->g_bk, M, inner, st));
     SF_TRY(launch_colsum(dV, bp->g_bv, M, inner, st));
-    SF_TRY(launch_gemm_tn_reduce(dQ, nq, bp->g_wq, M, inner, C, false, st));
-    SF_TRY(launch_gemm_tn_reduce(dK, nkv, bp->g_wk, M, inner, C, false, st));
-    SF_TRY(launch_gemm_tn_reduce(dV, nkv, bp->g_wv, M, inner, C, false, st));
+    SF_TRY(launch_gemm_tn_reduce(dQ, nq, bp->g_wq, M, inner, C, false, st, tf));
+    SF_TRY(launch_gemm_tn_reduce(dK, nkv, bp->g_wk, M, inner, C, false, st, tf));
+    SF_TRY(launch_gemm_tn_reduce(dV, nkv, bp->g_wv, M, inner, C, false, st, tf));
     // gradients w.r.t. the (normalised) operands
     float* gq_dst = need_q ? gnq : bp->g_q_src;
-    SF_TRY(launch_gemm_nn(dQ, p->wq, nullptr, gq_dst, M, C, inner, false, st));
+    SF_TRY(launch_gemm_nn(dQ, p->wq, nullptr, gq_dst, M, C, inner, false, st, tf));
     if (share) {
-        SF_TRY(launch_gemm_nn(dK, p->wk, nullptr, gq_dst, M, C, inner, true, st));
-        SF_TRY(launch_gemm_nn(dV, p->wv, nullptr, gq_dst, M, C, inner, true, st));
+        SF_TRY(launch_gemm_nn(dK, p->wk, nullptr, gq_dst, M, C, inner, true, st, tf));
+        SF_TRY(launch_gemm_nn(dV, p->wv, nullptr, gq_dst, M, C, inner, true, st, tf));
     } else {
         // distinct kv operand (other tensor and/or other LayerNorm)
         float* gkv_dst = need_kv ? gnkv : (bp->g_kv_src ? bp->g_kv_src : gnkv);
-        SF_TRY(launch_gemm_nn(dK, p->wk, nullptr, gkv_dst, M, C, inner, false, st));
-        SF_TRY(launch_gemm_nn(dV, p->wv, nullptr, gkv_dst, M, C, inner, true, st));
+        SF_TRY(launch_gemm_nn(dK, p->wk, nullptr, gkv_dst, M, C, inner, false, st, tf));
+        SF_TRY(launch_gemm_nn(dV, p->wv, nullptr, gkv_dst, M, C, inner, true, st, tf));
     }
     // ---- LayerNorm adjoints -----------------------------------------------------------------------------
     if (need_q) SF_TRY(launch_ln_bwd(p->q_src, p->ln_q_gamma, p->ln_q_beta, gnq, bp->g_q_src, bp->g_ln_q_gamma, bp->g_ln_q_beta, M, C, p->ln_eps, false, false, st));
@@ -599,6 +735,7 @@ size_t mlp_bwd_ws(const sf_mlp_bwd_params* bp) {
 }
 
 int mlp_bwd(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: TF32 tensor-core GEMMs in the backward pass
     const sf_mlp_params* p = &bp->fwd;
     const long long M = p->M;
     const int C = p->C, H = p->hidden;
@@ -614,12 +751,12 @@ int mlp_bwd(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStre
     g1.p[0] = GemmProblem{n, p->w1, p->b1, nullptr, hpre};
     SF_TRY(launch_gemm_tn(g1, 1, M, H, C, false, st));
     SF_TRY(launch_colsum(bp->gout, bp->g_b2, M, C, st));
-    SF_TRY(launch_gemm_tn_reduce(bp->gout, hpre, bp->g_w2, M, C, H, true, st));      // gW2 = gout^T ELU(hpre)
-    SF_TRY(launch_gemm_nn(bp->gout, p->w2, hpre, gh, M, H, C, false, st));           // g_hpre = (gout W2) o ELU'(hpre)
+    SF_TRY(launch_gemm_tn_reduce(bp->gout, hpre, bp->g_w2, M, C, H, true, st, tf));      // gW2 = gout^T ELU(hpre)
+    SF_TRY(launch_gemm_nn(bp->gout, p->w2, hpre, gh, M, H, C, false, st, tf));           // g_hpre = (gout W2) o ELU'(hpre)
     SF_TRY(launch_colsum(gh, bp->g_b1, M, H, st));
-    SF_TRY(launch_gemm_tn_reduce(gh, n, bp->g_w1, M, H, C, false, st));
+    SF_TRY(launch_gemm_tn_reduce(gh, n, bp->g_w1, M, H, C, false, st, tf));
     float* gdst = p->ln_gamma ? gn : bp->g_in;
-    SF_TRY(launch_gemm_nn(gh, p->w1, nullptr, gdst, M, C, H, false, st));
+    SF_TRY(launch_gemm_nn(gh, p->w1, nullptr, gdst, M, C, H, false, st, tf));
     if (p->ln_gamma) SF_TRY(launch_ln_bwd(p->in, p->ln_gamma, p->ln_beta, gn, bp->g_in, bp->g_ln_gamma, bp->g_ln_beta, M, C, p->ln_eps, false, false, st));
     return SF_OK;
 }
@@ -636,6 +773,7 @@ size_t patch_bwd_ws(const sf_patch_bwd_params* bp) {
 }
 
 int patch_bwd(const sf_patch_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: TF32 tensor-core GEMMs in the backward pass
     const sf_patch_params* p = &bp->fwd;
     const int mm = p->mh * p->mw;
     const long long Mr = p->encoder ? (long long)p->B * (p->H / p->mh) * (p->W / p->mw) : (long long)p->B * p->H * p->W;
@@ -657,12 +795,12 @@ int patch_bwd(const sf_patch_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cuda
     if (!p->encoder) { SF_TRY(sf_patch_merge(bp->gout, gpost, p->B, p->H * p->mh, p->W * p->mw, p->Cout, p->mh, p->mw, (void*)st)); gy = gpost; }
     SF_TRY(launch_ln_bwd(lin, p->ln_gamma, p->ln_beta, gy, glin, bp->g_ln_gamma, bp->g_ln_beta, Mr, N, p->ln_eps, true, false, st));
     SF_TRY(launch_colsum(glin, bp->g_b, Mr, N, st));
-    SF_TRY(launch_gemm_tn_reduce(glin, A, bp->g_w, Mr, N, K, false, st));
+    SF_TRY(launch_gemm_tn_reduce(glin, A, bp->g_w, Mr, N, K, false, st, tf));
     if (p->encoder) {
-        SF_TRY(launch_gemm_nn(glin, p->w, nullptr, gA, Mr, K, N, false, st));
+        SF_TRY(launch_gemm_nn(glin, p->w, nullptr, gA, Mr, K, N, false, st, tf));
         SF_TRY(sf_patch_unmerge(gA, bp->g_in, p->B, p->H / p->mh, p->W / p->mw, p->Cin, p->mh, p->mw, (void*)st));
     } else {
-        SF_TRY(launch_gemm_nn(glin, p->w, nullptr, bp->g_in, Mr, K, N, false, st));
+        SF_TRY(launch_gemm_nn(glin, p->w, nullptr, bp->g_in, Mr, K, N, false, st, tf));
     }
     return SF_OK;
 }
