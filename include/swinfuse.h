@@ -273,6 +273,30 @@ int sf_head_bwd(const sf_head_bwd_params* p, void* workspace, size_t workspace_b
 int sf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* Fusion loss of a008_loss.py (MyLoss.calcu_total_loss, a008:226-282, constants A000_CONFIG.py:34-52) and its
+ * gradient w.r.t. the fused image, SURVEY 8(a) row a19.  fusion / ir / vis: contiguous (B,1,H,W) fp32.
+ *   loss[0] = r_ssim * loss[1] + r_texture * loss[2] + r_intensity * loss[3]
+ *   loss[1] = ssim_scale * [w_ir MS(f, ir) + (1 - w_ir) MS(f, vis)]   (kornia MS_SSIMLoss() defaults, a008:24,109-110)
+ *   loss[2] = texture_scale * mean |Sobel(f) - max(Sobel(ir), Sobel(vis))|   (kornia Sobel() defaults, a008:37,187-198)
+ *   loss[3] = intensity_scale * mean |f - max(ir, vis)|                      (a008:218-224)
+ * f = clamp(fusion, 0, 1) when clamp01 != 0 (a016:153 clamps the model output before the loss; its gradient mask is
+ * then applied to g_fusion).  g_fusion (B,1,H,W) receives d loss[0] / d fusion; NULL = value only.
+ * The kornia arithmetic is restated (kornia is not vendored by the reference): see oracle/kornia_restatement.py. */
+typedef struct {
+    const float* fusion; const float* ir; const float* vis;
+    float* loss;        /* 4 floats */
+    float* total;       /* or NULL: a second copy of loss[0] (lets the caller own the scalar as its own buffer) */
+    float* g_fusion;    /* or NULL */
+    int B, H, W;
+    int clamp01;
+    float w_ir, ssim_scale, texture_scale, intensity_scale, r_ssim, r_texture, r_intensity;
+} sf_fusion_loss_params;
+size_t sf_fusion_loss_workspace_bytes(const sf_fusion_loss_params* p);
+int sf_fusion_loss(const sf_fusion_loss_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i] = in[i] * scalar[0]  (chain rule with the upstream gradient of the scalar loss, read on the device) */
+int sf_scale_by_scalar(const float* in, const float* scalar, float* out, long long n, void* stream);
+
 /* out[i] = a[i] + b[i]  (U-Net skip when no crop precedes it) */
 int sf_add(const float* a, const float* b, float* out, long long n, void* stream);
 

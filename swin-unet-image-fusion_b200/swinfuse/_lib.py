@@ -69,6 +69,13 @@ class HeadBwdParams(C.Structure):
         "gout", "g_x", "g_y", "g_w1", "g_b1", "g_bn_gamma", "g_bn_beta", "g_w2", "g_b2")]
 
 
+class FusionLossParams(C.Structure):
+    _fields_ = [(n, _f) for n in ("fusion", "ir", "vis", "loss", "total", "g_fusion")] + [
+        (n, C.c_int) for n in ("B", "H", "W", "clamp01")] + [
+        (n, C.c_float) for n in ("w_ir", "ssim_scale", "texture_scale", "intensity_scale", "r_ssim", "r_texture",
+                                 "r_intensity")]
+
+
 class ProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_longlong), ("total_ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
@@ -122,6 +129,9 @@ SIGNATURES = {
     "sf_head_bwd_workspace_bytes": (_sz, [C.POINTER(HeadBwdParams)]),
     "sf_head_bwd": (_i, [C.POINTER(HeadBwdParams), _f, _sz, _f]),
     "sf_add": (_i, [_f, _f, _f, _ll, _f]),
+    "sf_fusion_loss_workspace_bytes": (_sz, [C.POINTER(FusionLossParams)]),
+    "sf_fusion_loss": (_i, [C.POINTER(FusionLossParams), _f, _sz, _f]),
+    "sf_scale_by_scalar": (_i, [_f, _f, _f, _ll, _f]),
     "sf_adam_step": (_i, [_f, _f, _f, _f, _ll, _fl, _fl, _fl, _fl, _i, _fl, _f]),
 }
 

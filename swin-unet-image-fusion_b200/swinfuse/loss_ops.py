@@ -1,70 +1,90 @@
-"""Fusion loss of a008_loss.py -- INTERIM implementation.
+"""Fusion loss of a008_loss.py on the device: libswinfuse's sf_fusion_loss kernels.
 
-    L = 1/3 * 0.305 * [0.2 MS(f, ir) + 0.8 MS(f, vis)]
-      + 1/3 * 250   * mean |Sobel(f) - max(Sobel(ir), Sobel(vis))|
-      + 1/3 * 45    * mean |f - max(ir, vis)|                       (A000_CONFIG.py:34-52, a008:226-282)
+    L = r_s * ssim_scale * [w_ir MS(f, ir) + (1 - w_ir) MS(f, vis)]
+      + r_t * texture_scale * mean |Sobel(f) - max(Sobel(ir), Sobel(vis))|
+      + r_i * intensity_scale * mean |f - max(ir, vis)|          (A000_CONFIG.py:34-52, a008:226-282)
 
-Status: the arithmetic of MS-SSIM+L1 and Sobel lives in the third-party ``kornia`` package, which the
-reference does not pin and which is not installed here, so this is a from-memory restatement of the
-published algorithms (PARITY UNPINNED).  It is written with plain torch ops (cuDNN / ATen kernels),
-i.e. it is NOT one of this library's sm_100a kernels: SURVEY section 8(f) ranks the loss kernels as
-the next row to build after the model path.  It exists so that the training step (forward, loss,
-backward kernels, gradient all-reduce, Adam kernel) can be exercised and timed end to end.
-The two MS-SSIM calls share mu_f and E[f^2], the 3x-duplicated sigma channels are de-duplicated and the
-Gaussian windows are applied separably (mathematically identical to the kornia formulation).
+One C-ABI call computes the value (and the three scaled terms a016 logs) together with d L / d fusion; autograd only
+multiplies by the upstream scalar (sf_scale_by_scalar).  MS(.,.) and Sobel are kornia's MS_SSIMLoss() / Sobel() with
+default arguments, restated (kornia is not vendored or pinned by the reference: parity against kornia itself is
+unpinned, parity against oracle/kornia_restatement.py is tested on the GPU).  CUDA tensors only: no CPU path.
 """
 from __future__ import annotations
 
-import torch
-import torch.nn.functional as F
+import ctypes as C
 
-SIGMAS = (0.5, 1.0, 2.0, 4.0, 8.0)
-K1, K2, ALPHA, COMPENSATION, DATA_RANGE = 0.01, 0.03, 0.025, 200.0, 1.0
+import torch
+
+from . import _lib
+from ._lib import SwinFuseError, check
+
+
+def _check_inputs(fusion, ir, vis):
+    for name, t in (("fusion", fusion), ("ir", ir), ("vis", vis)):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise SwinFuseError(f"fusion loss: {name} must be a CUDA tensor (libswinfuse has no CPU path)")
+        if t.dtype != torch.float32:
+            raise SwinFuseError(f"fusion loss: {name} must be float32, got {t.dtype}")
+    if fusion.dim() != 4 or fusion.shape[1] != 1 or ir.shape != fusion.shape or vis.shape != fusion.shape:
+        raise SwinFuseError(f"fusion loss expects three (B,1,H,W) tensors, got {tuple(fusion.shape)}, "
+                            f"{tuple(ir.shape)}, {tuple(vis.shape)}")
+
+
+def _plane(t: torch.Tensor) -> torch.Tensor:
+    # one channel: NCHW-contiguous and channels-last memory coincide, .contiguous() is then free
+    return t.detach().contiguous()
+
+
+class _FusionLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fusion, ir, vis, cfg):
+        _check_inputs(fusion, ir, vis)
+        f, a, v = _plane(fusion), _plane(ir), _plane(vis)
+        b, _, h, w = f.shape
+        need_grad = fusion.requires_grad
+        out = torch.empty(4, dtype=torch.float32, device=f.device)
+        total = torch.empty((), dtype=torch.float32, device=f.device)
+        grad = torch.empty_like(f) if need_grad else None
+        p = _lib.FusionLossParams(f.data_ptr(), a.data_ptr(), v.data_ptr(), out.data_ptr(), total.data_ptr(),
+                                  None if grad is None else grad.data_ptr(), b, h, w, int(cfg["clamp01"]),
+                                  cfg["w_ir"], cfg["ssim_scale"], cfg["texture_scale"], cfg["intensity_scale"],
+                                  cfg["r_ssim"], cfg["r_texture"], cfg["r_intensity"])
+        lib = _lib.load()
+        nbytes = lib.sf_fusion_loss_workspace_bytes(C.byref(p))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=f.device)
+        check(lib.sf_fusion_loss(C.byref(p), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream),
+              "sf_fusion_loss")
+        ctx.grad = grad
+        ctx.fusion_shape = fusion.shape
+        ctx.mark_non_differentiable(out)
+        return total, out
+
+    @staticmethod
+    def backward(ctx, g_total, _g_terms):
+        if ctx.grad is None:
+            return None, None, None, None
+        g = torch.empty_like(ctx.grad)
+        gs = g_total.detach().to(torch.float32).contiguous()
+        check(_lib.load().sf_scale_by_scalar(ctx.grad.data_ptr(), gs.data_ptr(), g.data_ptr(), g.numel(),
+                                              torch.cuda.current_stream().cuda_stream), "sf_scale_by_scalar")
+        return g.view(ctx.fusion_shape), None, None, None
 
 
 class FusionLoss(torch.nn.Module):
+    """forward(fusion, ir, vis) -> scalar loss (a008 MyLoss.calcu_total_loss without the bookkeeping).
+
+    ``clamp01=True`` folds a016:153's ``torch.clamp(fusion, 0, 1)`` into the kernels (value and gradient mask).
+    ``last_terms`` holds the device tensor (total, ssim, texture, intensity) of the last call, scaled as a008 logs them."""
+
     def __init__(self, fus_ir_ssim_weight=0.2, ssim_scale=0.305, texture_scale=250.0, intensity_scale=45.0,
-                 ratios=(1 / 3, 1 / 3, 1 / 3)):
+                 ratios=(1 / 3, 1 / 3, 1 / 3), clamp01=False):
         super().__init__()
-        size = int(4 * SIGMAS[-1] + 1)
-        coords = torch.arange(size, dtype=torch.float32) - size // 2
-        g1 = torch.stack([torch.exp(-(coords ** 2) / (2 * s ** 2)) for s in SIGMAS])
-        g1 = g1 / g1.sum(dim=1, keepdim=True)
-        # the 33x33 Gaussian windows are outer products g g^T: applied as a vertical then a horizontal 33-tap pass
-        # (same zero padding, 16x fewer multiply-adds than the dense 2-D windows)
-        self.register_buffer("g_v", g1[:, None, :, None].contiguous())               # (5,1,33,1)
-        self.register_buffer("g_h", g1[:, None, None, :].contiguous())               # (5,1,1,33)
-        kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]) / 8.0
-        self.register_buffer("sobel", torch.stack([kx, kx.t()])[:, None])             # (2,1,3,3)
-        self.pad = size // 2
-        self.w_ir, self.ssim_scale, self.texture_scale, self.intensity_scale, self.ratios = \
-            fus_ir_ssim_weight, ssim_scale, texture_scale, intensity_scale, ratios
-        self.c1, self.c2 = (K1 * DATA_RANGE) ** 2, (K2 * DATA_RANGE) ** 2
-
-    def _blur(self, x):   # (B,1,H,W) -> (B,5,H,W), zero padding as kornia's MS_SSIMLoss
-        return F.conv2d(F.conv2d(x, self.g_v, padding=(self.pad, 0)), self.g_h, padding=(0, self.pad), groups=len(SIGMAS))
-
-    def _ms_ssim_l1(self, f, mu_f, e_ff, y):
-        mu_y, e_yy, e_fy = self._blur(y), self._blur(y * y), self._blur(f * y)
-        l = (2 * mu_f * mu_y + self.c1) / (mu_f * mu_f + mu_y * mu_y + self.c1)
-        cs = (2 * (e_fy - mu_f * mu_y) + self.c2) / ((e_ff - mu_f * mu_f) + (e_yy - mu_y * mu_y) + self.c2)
-        lm = l[:, -1] ** 3                      # the three duplicated sigma=8 channels
-        # every sigma appears three times; an explicit product (prod()'s backward inspects the input for zeros on
-        # the host, which breaks CUDA-graph capture of the training step)
-        pics = (cs[:, 0] * cs[:, 1] * cs[:, 2] * cs[:, 3] * cs[:, 4]) ** 3
-        d = (f - y).abs()
-        l1 = F.conv2d(F.conv2d(d, self.g_v[-1:], padding=(self.pad, 0)), self.g_h[-1:], padding=(0, self.pad))[:, 0]
-        return (COMPENSATION * (ALPHA * (1 - lm * pics) + (1 - ALPHA) * l1 / DATA_RANGE)).mean()
-
-    def _sobel_mag(self, x):
-        g = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="replicate"), self.sobel)
-        return torch.sqrt(g[:, 0:1] ** 2 + g[:, 1:2] ** 2 + 1e-6)
+        self.cfg = dict(w_ir=float(fus_ir_ssim_weight), ssim_scale=float(ssim_scale), texture_scale=float(texture_scale),
+                        intensity_scale=float(intensity_scale), r_ssim=float(ratios[0]), r_texture=float(ratios[1]),
+                        r_intensity=float(ratios[2]), clamp01=bool(clamp01))
+        self.last_terms = None
 
     def forward(self, fusion, ir, vis):
-        mu_f, e_ff = self._blur(fusion), self._blur(fusion * fusion)
-        ssim = (self.w_ir * self._ms_ssim_l1(fusion, mu_f, e_ff, ir)
-                + (1 - self.w_ir) * self._ms_ssim_l1(fusion, mu_f, e_ff, vis)) * self.ssim_scale
-        texture = (self._sobel_mag(fusion) - torch.max(self._sobel_mag(ir), self._sobel_mag(vis))).abs().mean() * self.texture_scale
-        intensity = (fusion - torch.max(ir, vis)).abs().mean() * self.intensity_scale
-        self.last_terms = (ssim.detach(), texture.detach(), intensity.detach())
-        return ssim * self.ratios[0] + texture * self.ratios[1] + intensity * self.ratios[2]
+        total, terms = _FusionLossFn.apply(fusion, ir, vis, self.cfg)
+        self.last_terms = terms
+        return total

@@ -111,7 +111,8 @@ class DataParallelTrainer:
     def _forward_backward(self, ir: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
         self.flat.zero_grad()
         fusion = self.model(ir, vis)
-        fusion = torch.clamp(fusion, 0, 1)
+        if not getattr(self.loss_fn, "cfg", {}).get("clamp01", False):   # FusionLoss(clamp01=True) clamps in its kernels
+            fusion = torch.clamp(fusion, 0, 1)
         loss = self.loss_fn(fusion, ir, vis)
         loss.backward()
         return loss.detach()

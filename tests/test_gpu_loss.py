@@ -1,0 +1,76 @@
+"""sf_fusion_loss on the GPU against the dense restatement of the a008 / kornia formulation
+(oracle/kornia_restatement.py, run on the CPU; kornia itself is not installed: parity against kornia is unpinned).
+Value, the three logged terms and the gradient w.r.t. the fused image; fp32 tolerance 2e-4 relative (the kernels
+sum 33-tap windows in a different order than the dense 33x33 convolution and use 1/den instead of a division)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "swin-unet-image-fusion_b200"))
+
+from oracle import kornia_restatement as kr  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-4
+
+
+def _oracle(x, ir, vis, clamp):
+    x = x.clone().requires_grad_(True)
+    f = torch.clamp(x, 0, 1) if clamp else x
+    ms, sob = kr.MS_SSIMLoss(), kr.Sobel()
+    total = kr.total_loss(f, ir, vis, ms, sob)
+    (g,) = torch.autograd.grad(total, x)
+    with torch.no_grad():
+        ssim = (0.2 * ms(f, ir) + 0.8 * ms(f, vis)) * 0.305
+        tex = (sob(f) - torch.max(sob(ir), sob(vis))).abs().mean() * 250
+        inten = (f - torch.max(ir, vis)).abs().mean() * 45
+    return total.detach(), torch.stack([total.detach(), ssim, tex, inten]), g
+
+
+@pytest.mark.parametrize("shape,clamp", [((2, 1, 48, 56), False), ((1, 1, 37, 131), True), ((3, 1, 20, 20), True),
+                                         ((2, 1, 256, 256), True), ((1, 1, 300, 129), False)])
+def test_fusion_loss_value_terms_and_gradient_match_the_dense_restatement(shape, clamp):
+    from swinfuse.loss_ops import FusionLoss
+    g = torch.Generator().manual_seed(11)
+    # the fused image leaves [0,1] on ~20% of the pixels so that the clamp (value and gradient mask) is exercised
+    x = torch.rand(shape, generator=g) * 1.25 - 0.125 if clamp else torch.rand(shape, generator=g)
+    ir, vis = torch.rand(shape, generator=g), torch.rand(shape, generator=g)
+    ref_total, ref_terms, ref_g = _oracle(x, ir, vis, clamp)
+    xd = x.cuda().requires_grad_(True)
+    fn = FusionLoss(clamp01=clamp)
+    total = fn(xd, ir.cuda(), vis.cuda())
+    (got_g,) = torch.autograd.grad(total * 1.0, xd)
+    terms = fn.last_terms.cpu()
+    assert abs(float(total) - float(ref_total)) <= TOL * abs(float(ref_total))
+    assert float((terms - ref_terms).abs().max()) <= TOL * float(ref_terms.abs().max())
+    assert float((got_g.cpu() - ref_g).abs().max()) <= TOL * float(ref_g.abs().max())
+    if clamp:
+        outside = (x < 0) | (x > 1)
+        assert outside.any() and float(got_g.cpu()[outside].abs().max()) == 0.0
+
+
+def test_fusion_loss_upstream_gradient_scales_and_value_only_mode():
+    from swinfuse.loss_ops import FusionLoss
+    g = torch.Generator().manual_seed(5)
+    x, ir, vis = (torch.rand(2, 1, 64, 64, generator=g).cuda() for _ in range(3))
+    fn = FusionLoss()
+    with torch.no_grad():
+        v0 = fn(x, ir, vis)
+    xg = x.clone().requires_grad_(True)
+    v1 = fn(xg, ir, vis)
+    (g1,) = torch.autograd.grad(v1, xg)
+    xg2 = x.clone().requires_grad_(True)
+    (g3,) = torch.autograd.grad(fn(xg2, ir, vis) * 3.0, xg2)
+    assert float(v0) == float(v1)                      # deterministic two-stage sums
+    assert torch.equal(g3, g1 * 3.0)
+
+
+def test_fusion_loss_rejects_cpu_tensors():
+    from swinfuse import SwinFuseError
+    from swinfuse.loss_ops import FusionLoss
+    x = torch.rand(1, 1, 32, 32)
+    with pytest.raises(SwinFuseError):
+        FusionLoss()(x, x, x)

@@ -1,4 +1,4 @@
-"""The training loss used by the data-parallel launcher (swinfuse/loss_ops.py: shared terms, de-duplicated
+"""The restructured loss the CUDA kernels follow (oracle/loss_separable_torch.py: shared terms, de-duplicated
 sigma channels, separable Gaussian windows) against the dense restatement of the a008 / kornia formulation
 (oracle/kornia_restatement.py, parity unpinned: kornia itself is not installed).  Value and gradient."""
 import os
@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "swin-unet-image-fusion_b200"))
 
 from oracle import kornia_restatement as kr  # noqa: E402
-from swinfuse.loss_ops import FusionLoss  # noqa: E402
+from oracle.loss_separable_torch import FusionLoss  # noqa: E402
 
 
 def test_fusion_loss_matches_dense_restatement_value_and_gradient():
