@@ -592,7 +592,10 @@ __global__ void __launch_bounds__(64) k_attn_core_bwd_w7(const float* __restrict
 }
 
 static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
-                                const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st) {
+                                const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st,
+                                bool tensor_cores) {
+    if (tensor_cores && attn_core_bwd_mma_supported(g, d))
+        return launch_attn_core_bwd_mma(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, d, st);
     const int tabn = (2 * g.wsh - 1) * (2 * g.wsw - 1);
     size_t smem = ((size_t)4 * g.T * d + 2 * (size_t)g.T * (g.T + 1) + 2 * tabn + 2) * sizeof(float) + (size_t)g.T * 12 + 16;
     SF_CHECK_ARG(smem <= 200 * 1024, "attention backward: window of %d tokens x head_dim %d needs %zu B of shared memory", g.T, d, smem);
@@ -691,7 +694,7 @@ int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws
     SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st, tf));
     SF_TRY(launch_gemm_nn(bp->gout, p->wo, nullptr, gO, M, inner, C, false, st, tf));
     // ---- attention core ---------------------------------------------------------------------------------
-    SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st));
+    SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, tf));
     // ---- projections --------------------------------------------------------------------------------------
     SF_TRY(launch_colsum(dQ, bp->g_bq, M, inner, st));
     SF_TRY(launch_colsum(dK, bp->g_bk, M, inner, st));

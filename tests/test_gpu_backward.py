@@ -222,3 +222,48 @@ def test_bf16_mode_gradients_track_the_fp32_ones():
     # sums with cancellation (the 13x13 bias tables) sit highest
     assert rel_l2 <= 1e-2, rel_l2
     assert worst[0] <= 1.5e-1, worst
+
+
+@pytest.mark.parametrize("c,nh,d", [(24, 8, 3), (48, 8, 6), (96, 8, 12)])
+@pytest.mark.parametrize("shifted", [False, True])
+@pytest.mark.parametrize("cross", [False, True])
+def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted, cross):
+    """SF_PREC_BF16 window attention runs its attention-core adjoint on mma.sync (fp16 operands, per-window power-of-two
+    normalisation of dO) and its GEMM adjoints on TF32; the backward recomputes the forward in fp32 in both modes, so the
+    gradients must agree with the exact fp32 backward to operand-rounding level (5e-3 of each tensor's scale), also for
+    upstream gradients as small as a mean-reduced loss produces (1e-7)."""
+    sw = dropin()
+    from a001_WindowAttention import WindowAttention
+    gen = torch.Generator().manual_seed(c + 2 * int(shifted) + int(cross))
+    wa = WindowAttention(in_out_dims=c, num_heads=nh, dims_per_head=d, window_size=(7, 7), use_cyclic_shift=shifted,
+                         use_cross_attention=cross, use_qkv_bias=True, attention_drop_ratio=0.0,
+                         linear_after_att_drop_ratio=0.0)
+    with torch.no_grad():
+        for prm in wa.parameters():
+            prm.copy_(torch.randn(prm.shape, generator=gen) * (0.3 if prm.dim() > 1 else 0.1))
+    wa = wa.cuda()
+    q0 = torch.randn(2, c, 21, 28, generator=gen)
+    kv0 = torch.randn(2, c, 21, 28, generator=gen)
+    gout = torch.randn(2, c, 21, 28, generator=gen) * 1e-7
+    res = {}
+    for prec in ("fp32", "bf16"):
+        sw.set_default_precision(prec)
+        try:
+            wa.zero_grad(set_to_none=True)
+            q = q0.cuda().requires_grad_(True)
+            kv = kv0.cuda().requires_grad_(True) if cross else q
+            out = wa(q, kv, kv)
+            (out * gout.cuda()).sum().backward()
+            r = {"gq": q.grad.cpu().clone()}
+            if cross:
+                r["gkv"] = kv.grad.cpu().clone()
+            for n, prm in wa.named_parameters():
+                r[n] = prm.grad.cpu().clone()
+            res[prec] = r
+        finally:
+            sw.set_default_precision("fp32")
+    gscale = max(float(v.abs().max()) for n, v in res["fp32"].items() if n not in ("gq", "gkv"))
+    for n, ref in res["fp32"].items():
+        floor = 0.05 * gscale if n not in ("gq", "gkv") else 0.0
+        e = float((res["bf16"][n] - ref).abs().max()) / max(float(ref.abs().max()), floor)
+        assert e <= 5e-3, (n, e)
