@@ -27,14 +27,14 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 struct __align__(16) ItemSmem {
     uint32_t q[64 * RSW], k[64 * RSW], v[64 * RSW], g[64 * RSW];
-    uint32_t qt[16 * TSW], kt[16 * TSW], gt[16 * TSW];
+    uint32_t qt[16 * TSW], kt[16 * TSW], gt[16 * TSW], vt[16 * TSW];
     float4 red[WARPS][14][32];      // per-warp partial dK^T / dV^T accumulator fragments
     long long rows2[2][T + 1];      // double-buffered by item parity: the tail of item i reads them while item i+1 is set up
     int reg2[2][64];
     float tab[176], gtab[176];
     float wmax[WARPS];
 };
-constexpr int OPERAND_WORDS = 4 * 64 * RSW + 3 * 16 * TSW;
+constexpr int OPERAND_WORDS = 4 * 64 * RSW + 4 * 16 * TSW;
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -89,15 +89,15 @@ __device__ __forceinline__ void store_flat(const float (&r)[NE], __half* rowmajo
 template <int D>
 __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                                                              const float* __restrict__ gO, float* __restrict__ dQ, float* __restrict__ dK,
-                                                             float* __restrict__ dV, const float* __restrict__ table, float* __restrict__ gtable,
-                                                             WinGeom g, int inner, int nh, float scale, long long nitems) {
+                                                             float* __restrict__ dV, float* __restrict__ O, const float* __restrict__ table,
+                                                             float* __restrict__ gtable, WinGeom g, int inner, int nh, float scale, long long nitems) {
     constexpr int NE = (T * D + WARPS * 32 - 1) / (WARPS * 32);
     constexpr int NDT = (D + 7) / 8;      // 8-wide dim tiles of dQ
     extern __shared__ __align__(16) unsigned char smraw[];
     ItemSmem* ws = reinterpret_cast<ItemSmem*>(smraw);
     const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
-        uint32_t* ops = reinterpret_cast<uint32_t*>(ws);                 // q, k, v, g, qt, kt, gt are contiguous
+        uint32_t* ops = reinterpret_cast<uint32_t*>(ws);                 // q, k, v, g, qt, kt, gt, vt are contiguous
         for (int i = threadIdx.x; i < OPERAND_WORDS; i += WARPS * 32) ops[i] = 0u;
     }
     ws->reg2[0][threadIdx.x & 63] = 0;
@@ -124,40 +124,59 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
 #pragma unroll
         for (int c = 0; c < 4; c++) tl[n][c] = 0.f;
 
+    // Software pipeline: the operand elements of the NEXT item are gathered into registers (pa..pd) while the current
+    // item is computed.  rows2 / reg2 are double-buffered by item parity.
+    float pa[NE], pb[NE], pc[NE], pd[NE];
+    if (blockIdx.x < nitems) {
+        const int win = (int)(blockIdx.x / nh), head = (int)(blockIdx.x - (long long)win * nh);
+        if (threadIdx.x < T) {
+            int rg;
+            ws->rows2[0][threadIdx.x] = win_token_src(g, win, threadIdx.x, &rg);
+            ws->reg2[0][threadIdx.x] = rg;
+        }
+        __syncthreads();
+        load_flat<D, NE>(gO, ws->rows2[0], inner, head * D, pd);
+        load_flat<D, NE>(Q, ws->rows2[0], inner, head * D, pa);
+        load_flat<D, NE>(K, ws->rows2[0], inner, head * D, pb);
+        load_flat<D, NE>(V, ws->rows2[0], inner, head * D, pc);
+    }
     int parity = 0;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
         const int win = (int)(item / nh), head = (int)(item - (long long)win * nh);
         const int hoff = head * D;
-        long long* rows = ws->rows2[parity];
-        int* reg = ws->reg2[parity];
-        if (threadIdx.x < T) {
-            int rg;
-            rows[threadIdx.x] = win_token_src(g, win, threadIdx.x, &rg);
-            reg[threadIdx.x] = rg;
-        }
-        __syncthreads();        // rows / regions visible; every warp is done with the previous item's operands and partials
+        const long long* rows = ws->rows2[parity];
+        const int* reg = ws->reg2[parity];
+        const long long nitem = item + gridDim.x;
+        const int nwin = (int)(nitem / nh), nhead = (int)(nitem - (long long)nwin * nh);
         float inv_sc;
         {
-            float a[NE], b[NE], c[NE], d[NE];
-            load_flat<D, NE>(gO, rows, inner, hoff, d);
-            load_flat<D, NE>(Q, rows, inner, hoff, a);
-            load_flat<D, NE>(K, rows, inner, hoff, b);
-            load_flat<D, NE>(V, rows, inner, hoff, c);
+            // every warp left the previous item's operands behind at its last barrier (the tail only reads `red` and rows)
             float mx = 0.f;
 #pragma unroll
-            for (int i = 0; i < NE; i++) mx = fmaxf(mx, fabsf(d[i]));
+            for (int i = 0; i < NE; i++) mx = fmaxf(mx, fabsf(pd[i]));
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) ws->wmax[m] = mx;
-            store_flat<D, NE>(a, reinterpret_cast<__half*>(ws->q), reinterpret_cast<__half*>(ws->qt), 1.f);
-            store_flat<D, NE>(b, reinterpret_cast<__half*>(ws->k), reinterpret_cast<__half*>(ws->kt), 1.f);
-            store_flat<D, NE>(c, reinterpret_cast<__half*>(ws->v), nullptr, 1.f);
+            store_flat<D, NE>(pa, reinterpret_cast<__half*>(ws->q), reinterpret_cast<__half*>(ws->qt), 1.f);
+            store_flat<D, NE>(pb, reinterpret_cast<__half*>(ws->k), reinterpret_cast<__half*>(ws->kt), 1.f);
+            store_flat<D, NE>(pc, reinterpret_cast<__half*>(ws->v), reinterpret_cast<__half*>(ws->vt), 1.f);
+            if (nitem < nitems && threadIdx.x < T) {     // token rows of the next item (other parity: the previous item's tail is over)
+                int rg;
+                ws->rows2[parity ^ 1][threadIdx.x] = win_token_src(g, nwin, threadIdx.x, &rg);
+                ws->reg2[parity ^ 1][threadIdx.x] = rg;
+            }
             __syncthreads();
             mx = fmaxf(fmaxf(ws->wmax[0], ws->wmax[1]), fmaxf(ws->wmax[2], ws->wmax[3]));
             const int ex = (__float_as_int(mx) >> 23) & 0xff;        // mx = 1.f * 2^(ex-127)
             const float sc = __int_as_float((254 - ex) << 23);        // 2^(127-ex): max |dO| * sc in [1, 2)
             inv_sc = __int_as_float(ex << 23);                        // (mx == 0: every output is 0 * 0)
-            store_flat<D, NE>(d, reinterpret_cast<__half*>(ws->g), reinterpret_cast<__half*>(ws->gt), sc);
+            store_flat<D, NE>(pd, reinterpret_cast<__half*>(ws->g), reinterpret_cast<__half*>(ws->gt), sc);
+            if (nitem < nitems) {
+                load_flat<D, NE>(gO, ws->rows2[parity ^ 1], inner, nhead * D, pd);
+                load_flat<D, NE>(Q, ws->rows2[parity ^ 1], inner, nhead * D, pa);
+                load_flat<D, NE>(K, ws->rows2[parity ^ 1], inner, nhead * D, pb);
+                load_flat<D, NE>(V, ws->rows2[parity ^ 1], inner, nhead * D, pc);
+            }
         }
         __syncthreads();
         const bool has_mask = reg[0] != reg[T - 1];   // region ids grow along both axes of a window
@@ -236,6 +255,34 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
             }
             ph[n][0] = pack_h2(s[n][0], s[n][1]); ph[n][1] = pack_h2(s[n][2], s[n][3]);
             dsh[n][0] = pack_h2(dp[n][0], dp[n][1]); dsh[n][1] = pack_h2(dp[n][2], dp[n][3]);
+        }
+        // ---- O rows of this tile = P V (the forward output the projection's weight gradient needs; the forward saves nothing)
+        if (O) {
+            float o[NDT][4];
+#pragma unroll
+            for (int nd = 0; nd < NDT; nd++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) o[nd][c] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const uint32_t a0 = ph[2 * kk][0], a1 = ph[2 * kk][1];
+                const uint32_t a2 = kk < 3 ? ph[(2 * kk + 1) % 7][0] : 0u, a3 = kk < 3 ? ph[(2 * kk + 1) % 7][1] : 0u;
+#pragma unroll
+                for (int nd = 0; nd < NDT; nd++) {
+                    const int kr = (8 * nd + gq) * TSW + 8 * kk + tq;
+                    mma16816(o[nd], a0, a1, a2, a3, ws->vt[kr], ws->vt[kr + 4]);
+                }
+            }
+#pragma unroll
+            for (int nd = 0; nd < NDT; nd++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int dd = 8 * nd + 2 * tq + e;
+                    if (dd < D) {
+                        if (r0 < T) O[rows[r0] * inner + hoff + dd] = o[nd][e];
+                        if (r1 < T) O[rows[r1] * inner + hoff + dd] = o[nd][2 + e];
+                    }
+                }
         }
         // ---- dQ rows of this tile = scale * dS K   (k index = key: tiles 2kk, 2kk+1 of dS form one 16-deep slice)
         {
@@ -319,7 +366,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
 }
 
 template <int D>
-int launch_one(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, const float* table,
+int launch_one(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O, const float* table,
                float* gtable, const WinGeom& g, int inner, int nh, long long nitems, cudaStream_t st) {
     const size_t smem = sizeof(ItemSmem);
     static thread_local bool configured = false;
@@ -330,7 +377,7 @@ int launch_one(const float* Q, const float* K, const float* V, const float* gO, 
     }
     long long grid = 148LL * 4;
     if (grid > nitems) grid = nitems;
-    k_attn_bwd_mma<D><<<(unsigned)grid, WARPS * 32, smem, st>>>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, 1.0f / sqrtf((float)D), nitems);
+    k_attn_bwd_mma<D><<<(unsigned)grid, WARPS * 32, smem, st>>>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, 1.0f / sqrtf((float)D), nitems);
     SF_CHECK_LAUNCH("bwd_attn_core_mma");
     return SF_OK;
 }
@@ -339,15 +386,15 @@ int launch_one(const float* Q, const float* K, const float* V, const float* gO, 
 
 bool attn_core_bwd_mma_supported(const WinGeom& g, int d) { return g.wsh == 7 && g.wsw == 7 && (d == 3 || d == 6 || d == 12); }
 
-int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
+int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
                              const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st) {
     const long long nitems = (long long)g.B * g.nWh * g.nWw * nh;
     const double mtok = (double)g.B * g.Hp * g.Wp;
-    ProfScope ps(prof_name("bwd_attn_core_mma_d%d", d), 12.0 * g.T * mtok * inner, 28.0 * mtok * inner, st);
+    ProfScope ps(prof_name("bwd_attn_core_mma_d%d", d), (O ? 14.0 : 12.0) * g.T * mtok * inner, (O ? 32.0 : 28.0) * mtok * inner, st);
     switch (d) {
-        case 3: return launch_one<3>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, nitems, st);
-        case 6: return launch_one<6>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, nitems, st);
-        case 12: return launch_one<12>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, nitems, st);
+        case 3: return launch_one<3>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
+        case 6: return launch_one<6>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
+        case 12: return launch_one<12>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
     }
     set_error("attention backward (mma): head_dim %d is not built", d);
     return SF_ERR_INVALID;

