@@ -1,5 +1,5 @@
-// Attention-core backward on tensor cores for 7x7 windows and head_dim <= 16 (stages 0-2 of the default model:
-// d = 3, 6, 12 -- 83 % of the backward attention work).  Adjoint of a001:317-354:
+// Attention-core backward on tensor cores for 7x7 windows and the head dims of the default model (d = 3, 6, 12, 24, 48;
+// the head dimension is processed in chunks of 16).  Adjoint of a001:317-354:
 //   P = softmax(scale Q K^T + bias -> mask) ; dV = P^T dO ; dP = dO V^T ; dS = P o (dP - rowsum(P o dP)) ;
 //   dtable[idx(i,j)] += dS ; dQ = scale dS K ; dK = scale dS^T Q.
 // One CTA of four warps owns one (window, head) at a time; warp m owns the 16-query tile m.  The q/k/v/dO rows (gathered through the shift + window-partition
@@ -25,16 +25,18 @@ constexpr int TSW = 36;     // transposed operand row = 72 halves = 36 words (64
 constexpr int WARPS = 4;
 constexpr float LOG2E = 1.4426950408889634f;
 
+// the head dimension is handled in KC chunks of 16 (d = 24 -> 2, d = 48 -> 3): every operand array exists per chunk
+template <int KC>
 struct __align__(16) ItemSmem {
-    uint32_t q[64 * RSW], k[64 * RSW], v[64 * RSW], g[64 * RSW];
-    uint32_t qt[16 * TSW], kt[16 * TSW], gt[16 * TSW], vt[16 * TSW];
+    uint32_t q[KC][64 * RSW], k[KC][64 * RSW], v[KC][64 * RSW], g[KC][64 * RSW];
+    uint32_t qt[KC][16 * TSW], kt[KC][16 * TSW], gt[KC][16 * TSW], vt[KC][16 * TSW];
     float4 red[WARPS][14][32];      // per-warp partial dK^T / dV^T accumulator fragments
     long long rows2[2][T + 1];      // double-buffered by item parity: the tail of item i reads them while item i+1 is set up
     int reg2[2][64];
     float tab[176], gtab[176];
     float wmax[WARPS];
 };
-constexpr int OPERAND_WORDS = 4 * 64 * RSW + 4 * 16 * TSW;
+constexpr int OPERAND_WORDS = 4 * 64 * RSW + 4 * 16 * TSW;   // per chunk
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -78,8 +80,9 @@ __device__ __forceinline__ void store_flat(const float (&r)[NE], __half* rowmajo
         const int tk = e / D, dd = e - tk * D;
         if (e < T * D) {
             const __half h = __float2half_rn(r[i] * mul);
-            rowmajor[tk * 2 * RSW + dd] = h;
-            if (transposed) transposed[dd * 2 * TSW + tk] = h;
+            const int c = dd >> 4, dl = dd & 15;           // chunk, dim inside the chunk
+            rowmajor[c * (64 * 2 * RSW) + tk * 2 * RSW + dl] = h;
+            transposed[c * (16 * 2 * TSW) + dl * 2 * TSW + tk] = h;
         }
     }
 }
@@ -87,18 +90,18 @@ __device__ __forceinline__ void store_flat(const float (&r)[NE], __half* rowmajo
 // One CTA (4 warps) per (window, head); warp m owns query rows 16 m .. 16 m + 15, so every lane meets the same 28
 // (query, key) positions on every item and the bias-table gradient is accumulated in 28 registers.
 template <int D>
-__global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+__global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                                                              const float* __restrict__ gO, float* __restrict__ dQ, float* __restrict__ dK,
                                                              float* __restrict__ dV, float* __restrict__ O, const float* __restrict__ table,
                                                              float* __restrict__ gtable, WinGeom g, int inner, int nh, float scale, long long nitems) {
     constexpr int NE = (T * D + WARPS * 32 - 1) / (WARPS * 32);
-    constexpr int NDT = (D + 7) / 8;      // 8-wide dim tiles of dQ
+    constexpr int KC = (D + 15) / 16;     // 16-wide chunks of the head dimension
     extern __shared__ __align__(16) unsigned char smraw[];
-    ItemSmem* ws = reinterpret_cast<ItemSmem*>(smraw);
+    ItemSmem<KC>* ws = reinterpret_cast<ItemSmem<KC>*>(smraw);
     const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
         uint32_t* ops = reinterpret_cast<uint32_t*>(ws);                 // q, k, v, g, qt, kt, gt, vt are contiguous
-        for (int i = threadIdx.x; i < OPERAND_WORDS; i += WARPS * 32) ops[i] = 0u;
+        for (int i = threadIdx.x; i < KC * OPERAND_WORDS; i += WARPS * 32) ops[i] = 0u;
     }
     ws->reg2[0][threadIdx.x & 63] = 0;
     ws->reg2[1][threadIdx.x & 63] = 0;
@@ -157,9 +160,9 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) ws->wmax[m] = mx;
-            store_flat<D, NE>(pa, reinterpret_cast<__half*>(ws->q), reinterpret_cast<__half*>(ws->qt), 1.f);
-            store_flat<D, NE>(pb, reinterpret_cast<__half*>(ws->k), reinterpret_cast<__half*>(ws->kt), 1.f);
-            store_flat<D, NE>(pc, reinterpret_cast<__half*>(ws->v), reinterpret_cast<__half*>(ws->vt), 1.f);
+            store_flat<D, NE>(pa, reinterpret_cast<__half*>(ws->q[0]), reinterpret_cast<__half*>(ws->qt[0]), 1.f);
+            store_flat<D, NE>(pb, reinterpret_cast<__half*>(ws->k[0]), reinterpret_cast<__half*>(ws->kt[0]), 1.f);
+            store_flat<D, NE>(pc, reinterpret_cast<__half*>(ws->v[0]), reinterpret_cast<__half*>(ws->vt[0]), 1.f);
             if (nitem < nitems && threadIdx.x < T) {     // token rows of the next item (other parity: the previous item's tail is over)
                 int rg;
                 ws->rows2[parity ^ 1][threadIdx.x] = win_token_src(g, nwin, threadIdx.x, &rg);
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
             const int ex = (__float_as_int(mx) >> 23) & 0xff;        // mx = 1.f * 2^(ex-127)
             const float sc = __int_as_float((254 - ex) << 23);        // 2^(127-ex): max |dO| * sc in [1, 2)
             inv_sc = __int_as_float(ex << 23);                        // (mx == 0: every output is 0 * 0)
-            store_flat<D, NE>(pd, reinterpret_cast<__half*>(ws->g), reinterpret_cast<__half*>(ws->gt), sc);
+            store_flat<D, NE>(pd, reinterpret_cast<__half*>(ws->g[0]), reinterpret_cast<__half*>(ws->gt[0]), sc);
             if (nitem < nitems) {
                 load_flat<D, NE>(gO, ws->rows2[parity ^ 1], inner, nhead * D, pd);
                 load_flat<D, NE>(Q, ws->rows2[parity ^ 1], inner, nhead * D, pa);
@@ -192,16 +195,21 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
                 }
         }
         float s[7][4], dp[7][4];
-        {
-            const uint32_t qa0 = ws->q[r0 * RSW + tq], qa1 = ws->q[r1 * RSW + tq], qa2 = ws->q[r0 * RSW + tq + 4], qa3 = ws->q[r1 * RSW + tq + 4];
-            const uint32_t ga0 = ws->g[r0 * RSW + tq], ga1 = ws->g[r1 * RSW + tq], ga2 = ws->g[r0 * RSW + tq + 4], ga3 = ws->g[r1 * RSW + tq + 4];
+#pragma unroll
+        for (int n = 0; n < 7; n++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) { s[n][c] = 0.f; dp[n][c] = 0.f; }
+#pragma unroll
+        for (int kc = 0; kc < KC; kc++) {
+            const uint32_t* qh = ws->q[kc];
+            const uint32_t* gh = ws->g[kc];
+            const uint32_t qa0 = qh[r0 * RSW + tq], qa1 = qh[r1 * RSW + tq], qa2 = qh[r0 * RSW + tq + 4], qa3 = qh[r1 * RSW + tq + 4];
+            const uint32_t ga0 = gh[r0 * RSW + tq], ga1 = gh[r1 * RSW + tq], ga2 = gh[r0 * RSW + tq + 4], ga3 = gh[r1 * RSW + tq + 4];
 #pragma unroll
             for (int n = 0; n < 7; n++) {
-#pragma unroll
-                for (int c = 0; c < 4; c++) { s[n][c] = 0.f; dp[n][c] = 0.f; }
                 const int kr = (8 * n + gq) * RSW + tq;
-                mma16816(s[n], qa0, qa1, qa2, qa3, ws->k[kr], ws->k[kr + 4]);
-                mma16816(dp[n], ga0, ga1, ga2, ga3, ws->v[kr], ws->v[kr + 4]);
+                mma16816(s[n], qa0, qa1, qa2, qa3, ws->k[kc][kr], ws->k[kc][kr + 4]);
+                mma16816(dp[n], ga0, ga1, ga2, ga3, ws->v[kc][kr], ws->v[kc][kr + 4]);
             }
         }
         // ---- softmax rows r0 (c = 0,1) and r1 (c = 2,3)
@@ -257,95 +265,91 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
             dsh[n][0] = pack_h2(dp[n][0], dp[n][1]); dsh[n][1] = pack_h2(dp[n][2], dp[n][3]);
         }
         // ---- O rows of this tile = P V (the forward output the projection's weight gradient needs; the forward saves nothing)
-        if (O) {
-            float o[NDT][4];
+        //      and dQ rows = scale * dS K; k index = key: tiles 2kk, 2kk+1 of P / dS form one 16-deep slice
 #pragma unroll
-            for (int nd = 0; nd < NDT; nd++)
+        for (int kc = 0; kc < KC; kc++) {
+            constexpr int NDT_MAX = 2;
+            const int ndt = (D - 16 * kc >= 9) ? 2 : 1;        // 8-wide dim tiles present in this chunk (compile time after unrolling)
+            float o[NDT_MAX][4], dq[NDT_MAX][4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) o[nd][c] = 0.f;
+            for (int nd = 0; nd < NDT_MAX; nd++)
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const uint32_t a0 = ph[2 * kk][0], a1 = ph[2 * kk][1];
-                const uint32_t a2 = kk < 3 ? ph[(2 * kk + 1) % 7][0] : 0u, a3 = kk < 3 ? ph[(2 * kk + 1) % 7][1] : 0u;
-#pragma unroll
-                for (int nd = 0; nd < NDT; nd++) {
-                    const int kr = (8 * nd + gq) * TSW + 8 * kk + tq;
-                    mma16816(o[nd], a0, a1, a2, a3, ws->vt[kr], ws->vt[kr + 4]);
-                }
-            }
-#pragma unroll
-            for (int nd = 0; nd < NDT; nd++)
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int dd = 8 * nd + 2 * tq + e;
-                    if (dd < D) {
-                        if (r0 < T) O[rows[r0] * inner + hoff + dd] = o[nd][e];
-                        if (r1 < T) O[rows[r1] * inner + hoff + dd] = o[nd][2 + e];
-                    }
-                }
-        }
-        // ---- dQ rows of this tile = scale * dS K   (k index = key: tiles 2kk, 2kk+1 of dS form one 16-deep slice)
-        {
-            float dq[NDT][4];
-#pragma unroll
-            for (int nd = 0; nd < NDT; nd++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) dq[nd][c] = 0.f;
+                for (int c = 0; c < 4; c++) { o[nd][c] = 0.f; dq[nd][c] = 0.f; }
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
+                const uint32_t p0 = ph[2 * kk][0], p1 = ph[2 * kk][1];
+                const uint32_t p2 = kk < 3 ? ph[(2 * kk + 1) % 7][0] : 0u, p3 = kk < 3 ? ph[(2 * kk + 1) % 7][1] : 0u;
                 const uint32_t a0 = dsh[2 * kk][0], a1 = dsh[2 * kk][1];
                 const uint32_t a2 = kk < 3 ? dsh[(2 * kk + 1) % 7][0] : 0u, a3 = kk < 3 ? dsh[(2 * kk + 1) % 7][1] : 0u;
 #pragma unroll
-                for (int nd = 0; nd < NDT; nd++) {
+                for (int nd = 0; nd < NDT_MAX; nd++) {
+                    if (nd >= ndt) continue;
                     const int kr = (8 * nd + gq) * TSW + 8 * kk + tq;
-                    mma16816(dq[nd], a0, a1, a2, a3, ws->kt[kr], ws->kt[kr + 4]);
+                    if (O) mma16816(o[nd], p0, p1, p2, p3, ws->vt[kc][kr], ws->vt[kc][kr + 4]);
+                    mma16816(dq[nd], a0, a1, a2, a3, ws->kt[kc][kr], ws->kt[kc][kr + 4]);
                 }
             }
             const float f = scale * inv_sc;
 #pragma unroll
-            for (int nd = 0; nd < NDT; nd++)
+            for (int nd = 0; nd < NDT_MAX; nd++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const int dd = 8 * nd + 2 * tq + e;
-                    if (dd < D) {
-                        if (r0 < T) dQ[rows[r0] * inner + hoff + dd] = dq[nd][e] * f;
-                        if (r1 < T) dQ[rows[r1] * inner + hoff + dd] = dq[nd][2 + e] * f;
+                    const int dd = 16 * kc + 8 * nd + 2 * tq + e;
+                    if (nd < ndt && dd < D) {
+                        if (r0 < T) {
+                            const long long o0 = rows[r0] * inner + hoff + dd;
+                            dQ[o0] = dq[nd][e] * f;
+                            if (O) O[o0] = o[nd][e];
+                        }
+                        if (r1 < T) {
+                            const long long o1 = rows[r1] * inner + hoff + dd;
+                            dQ[o1] = dq[nd][2 + e] * f;
+                            if (O) O[o1] = o[nd][2 + e];
+                        }
                     }
                 }
         }
-        // ---- partial dK^T = Q^T dS, dV^T = dO^T P over this warp's 16 queries (M = head dim, N = keys)
-        {
-            const int ar = gq * TSW + 8 * m + tq;
-            const uint32_t qa0 = ws->qt[ar], qa1 = ws->qt[ar + 8 * TSW], qa2 = ws->qt[ar + 4], qa3 = ws->qt[ar + 8 * TSW + 4];
-            const uint32_t ga0 = ws->gt[ar], ga1 = ws->gt[ar + 8 * TSW], ga2 = ws->gt[ar + 4], ga3 = ws->gt[ar + 8 * TSW + 4];
+        // ---- dK^T = Q^T dS, dV^T = dO^T P per 16-wide chunk of the head dimension (M = head dim, N = keys, K = queries):
+        //      every warp contributes the partial over its 16 queries, the four partials are summed through `red`
 #pragma unroll
-            for (int n = 0; n < 7; n++) {
-                float pk[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
-                mma16816(pk, qa0, qa1, qa2, qa3, movm_trans(dsh[n][0]), movm_trans(dsh[n][1]));
-                mma16816(pv, ga0, ga1, ga2, ga3, movm_trans(ph[n][0]), movm_trans(ph[n][1]));
-                ws->red[m][n][lane] = make_float4(pk[0], pk[1], pk[2], pk[3]);
-                ws->red[m][7 + n][lane] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-            }
-        }
-        __syncthreads();
-        // ---- sum the four partials; warp m finishes fragments m, m+4, m+8, m+12: (row = dim gq / gq+8, col = key 8 n + 2 tq + e)
+        for (int kc = 0; kc < KC; kc++) {
+            {
+                const int ar = gq * TSW + 8 * m + tq;
+                const uint32_t* qth = ws->qt[kc];
+                const uint32_t* gth = ws->gt[kc];
+                const uint32_t qa0 = qth[ar], qa1 = qth[ar + 8 * TSW], qa2 = qth[ar + 4], qa3 = qth[ar + 8 * TSW + 4];
+                const uint32_t ga0 = gth[ar], ga1 = gth[ar + 8 * TSW], ga2 = gth[ar + 4], ga3 = gth[ar + 8 * TSW + 4];
 #pragma unroll
-        for (int i = m; i < 14; i += WARPS) {
-            const float4 p0 = ws->red[0][i][lane], p1 = ws->red[1][i][lane], p2 = ws->red[2][i][lane], p3 = ws->red[3][i][lane];
-            const float acc[4] = {(p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w)};
-            const bool isk = i < 7;
-            const int n = isk ? i : i - 7;
-            float* dst = isk ? dK : dV;
-            const float f = isk ? scale * inv_sc : inv_sc;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int key = 8 * n + 2 * tq + e;
-                if (key < T) {
-                    const long long o = rows[key] * inner + hoff;
-                    if (gq < D) dst[o + gq] = acc[e] * f;
-                    if (gq + 8 < D) dst[o + gq + 8] = acc[2 + e] * f;
+                for (int n = 0; n < 7; n++) {
+                    float pk[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma16816(pk, qa0, qa1, qa2, qa3, movm_trans(dsh[n][0]), movm_trans(dsh[n][1]));
+                    mma16816(pv, ga0, ga1, ga2, ga3, movm_trans(ph[n][0]), movm_trans(ph[n][1]));
+                    ws->red[m][n][lane] = make_float4(pk[0], pk[1], pk[2], pk[3]);
+                    ws->red[m][7 + n][lane] = make_float4(pv[0], pv[1], pv[2], pv[3]);
                 }
             }
+            __syncthreads();
+            // warp m finishes fragments m, m+4, m+8, m+12: (row = dim gq / gq+8 of the chunk, col = key 8 n + 2 tq + e)
+#pragma unroll
+            for (int i = m; i < 14; i += WARPS) {
+                const float4 p0 = ws->red[0][i][lane], p1 = ws->red[1][i][lane], p2 = ws->red[2][i][lane], p3 = ws->red[3][i][lane];
+                const float acc[4] = {(p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w)};
+                const bool isk = i < 7;
+                const int n = isk ? i : i - 7;
+                float* dst = isk ? dK : dV;
+                const float f = isk ? scale * inv_sc : inv_sc;
+                const int d0 = 16 * kc + gq;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int key = 8 * n + 2 * tq + e;
+                    if (key < T) {
+                        const long long o = rows[key] * inner + hoff;
+                        if (d0 < D) dst[o + d0] = acc[e] * f;
+                        if (d0 + 8 < D) dst[o + d0 + 8] = acc[2 + e] * f;
+                    }
+                }
+            }
+            if (kc + 1 < KC) __syncthreads();     // `red` is rewritten by the next chunk (the next item passes two barriers first)
         }
     }
     // ---- table gradient: registers -> shared -> one global atomic per entry and CTA
@@ -368,14 +372,14 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_attn_bwd_mma(const float* __r
 template <int D>
 int launch_one(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O, const float* table,
                float* gtable, const WinGeom& g, int inner, int nh, long long nitems, cudaStream_t st) {
-    const size_t smem = sizeof(ItemSmem);
+    const size_t smem = sizeof(ItemSmem<(D + 15) / 16>);
     static thread_local bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_attn_bwd_mma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("attention backward (mma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
         configured = true;
     }
-    long long grid = 148LL * 4;
+    long long grid = 148LL * (D <= 16 ? 4 : 2);
     if (grid > nitems) grid = nitems;
     k_attn_bwd_mma<D><<<(unsigned)grid, WARPS * 32, smem, st>>>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, 1.0f / sqrtf((float)D), nitems);
     SF_CHECK_LAUNCH("bwd_attn_core_mma");
@@ -384,7 +388,7 @@ int launch_one(const float* Q, const float* K, const float* V, const float* gO, 
 
 }  // namespace
 
-bool attn_core_bwd_mma_supported(const WinGeom& g, int d) { return g.wsh == 7 && g.wsw == 7 && (d == 3 || d == 6 || d == 12); }
+bool attn_core_bwd_mma_supported(const WinGeom& g, int d) { return g.wsh == 7 && g.wsw == 7 && (d == 3 || d == 6 || d == 12 || d == 24 || d == 48); }
 
 int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
                              const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st) {
@@ -395,6 +399,8 @@ int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, con
         case 3: return launch_one<3>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
         case 6: return launch_one<6>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
         case 12: return launch_one<12>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
+        case 24: return launch_one<24>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
+        case 48: return launch_one<48>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
     }
     set_error("attention backward (mma): head_dim %d is not built", d);
     return SF_ERR_INVALID;

@@ -277,8 +277,110 @@ __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ 
     }
 }
 
+// Short rows (C <= 128, C % 4 == 0): a group of G lanes (8, 16 or 32) owns one row, four consecutive channels per lane
+// (128-bit accesses), so a warp works on 32 / G rows at once, the row reductions are log2(G) shuffle steps, and the
+// lane's channels never change: ggamma / gbeta partial sums stay in eight registers until the end of the kernel.
+template <int G, bool ELUOUT, bool ACCUM>
+__global__ void __launch_bounds__(256) k_ln_bwd_grp(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const float* __restrict__ gy, float* __restrict__ gx, float* __restrict__ ggamma,
+                                                    float* __restrict__ gbeta, long long M, int C, float eps) {
+    __shared__ float sacc[8][2][128];
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = (lane % G) * 4, sub = lane / G;
+    const bool act = c0 < C;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 gm = act ? __ldg(reinterpret_cast<const float4*>(gamma + c0)) : z4;
+    const float4 bt = act ? __ldg(reinterpret_cast<const float4*>(beta + c0)) : z4;
+    const float invC = 1.f / (float)C;
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long wstride = (long long)gridDim.x * 8 * RPW;
+    for (long long base = ((long long)blockIdx.x * 8 + warp) * RPW; base < M; base += wstride) {
+        const long long row = base + sub;
+        const bool ok = act && row < M;
+        const float4 xv = ok ? __ldg(reinterpret_cast<const float4*>(x + row * C + c0)) : z4;
+        float4 gv = ok ? __ldg(reinterpret_cast<const float4*>(gy + row * C + c0)) : z4;
+        float sx = (xv.x + xv.y) + (xv.z + xv.w);
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        const float mean = sx * invC;
+        float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
+        if (!act) { d0 = 0.f; d1 = 0.f; d2 = 0.f; d3 = 0.f; }
+        float var = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float rstd = rsqrtf(var * invC + eps);
+        const float h0 = d0 * rstd, h1 = d1 * rstd, h2 = d2 * rstd, h3 = d3 * rstd;
+        if (ELUOUT) {
+            gv.x *= elu_grad(h0 * gm.x + bt.x); gv.y *= elu_grad(h1 * gm.y + bt.y);
+            gv.z *= elu_grad(h2 * gm.z + bt.z); gv.w *= elu_grad(h3 * gm.w + bt.w);
+        }
+        const float g0 = gv.x * gm.x, g1 = gv.y * gm.y, g2 = gv.z * gm.z, g3 = gv.w * gm.w;
+        float s1 = (g0 + g1) + (g2 + g3), s2 = (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        s1 *= invC; s2 *= invC;
+        if (ok) {
+            float4 o4 = make_float4(rstd * (g0 - s1 - h0 * s2), rstd * (g1 - s1 - h1 * s2), rstd * (g2 - s1 - h2 * s2), rstd * (g3 - s1 - h3 * s2));
+            float4* dst = reinterpret_cast<float4*>(gx + row * C + c0);
+            if (ACCUM) { const float4 old = *dst; o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w; }
+            *dst = o4;
+            ag[0] = fmaf(gv.x, h0, ag[0]); ag[1] = fmaf(gv.y, h1, ag[1]); ag[2] = fmaf(gv.z, h2, ag[2]); ag[3] = fmaf(gv.w, h3, ag[3]);
+            ab[0] += gv.x; ab[1] += gv.y; ab[2] += gv.z; ab[3] += gv.w;
+        }
+    }
+    // lanes of the other row groups of the warp hold the same channels
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            ag[j] += __shfl_xor_sync(0xffffffffu, ag[j], o);
+            ab[j] += __shfl_xor_sync(0xffffffffu, ab[j], o);
+        }
+    if (sub == 0 && act) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { sacc[warp][0][c0 + j] = ag[j]; sacc[warp][1][c0 + j] = ab[j]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { a += sacc[w][0][c]; b += sacc[w][1][c]; }
+        if (ggamma) atomicAdd(&ggamma[c], a);
+        if (gbeta) atomicAdd(&gbeta[c], b);
+    }
+}
+
+template <int G>
+static void launch_ln_bwd_grp(const float* x, const float* gamma, const float* beta, const float* gy, float* gx, float* ggamma, float* gbeta,
+                              long long M, int C, float eps, bool eluout, bool accum, cudaStream_t st) {
+    const long long rows_per_block = 8 * (32 / G);
+    long long blocks = (M + rows_per_block - 1) / rows_per_block;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    if (eluout) {
+        if (accum) k_ln_bwd_grp<G, true, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd_grp<G, true, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+    } else {
+        if (accum) k_ln_bwd_grp<G, false, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd_grp<G, false, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+    }
+}
+
 static int launch_ln_bwd(const float* x, const float* gamma, const float* beta, const float* gy, float* gx, float* ggamma,
                          float* gbeta, long long M, int C, float eps, bool eluout, bool accum, cudaStream_t st) {
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx) |
+                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    if (C <= 128 && (C & 3) == 0 && al16) {
+        ProfScope ps("bwd_layernorm", 20.0 * (double)M * C, 12.0 * (double)M * C, st);
+        if (C <= 32) launch_ln_bwd_grp<8>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps, eluout, accum, st);
+        else if (C <= 64) launch_ln_bwd_grp<16>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps, eluout, accum, st);
+        else launch_ln_bwd_grp<32>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps, eluout, accum, st);
+        SF_CHECK_LAUNCH("bwd_layernorm");
+        return SF_OK;
+    }
     const int threads = 256;
     long long blocks = (M * 32 + threads - 1) / threads;
     if (blocks > 148LL * 4) blocks = 148LL * 4;

@@ -50,11 +50,12 @@ __device__ __forceinline__ float4 ld4(const float* __restrict__ base, long long 
 
 struct RowsBatch { const float* A[3]; const float* B[3]; const float* bias[3]; float* C[3]; };
 
-// grid (ceil(M/64), ceil(N/64), nbatch); reduction over K in slices of 16
+// grid (ceil(M/64), ceil(N/64), nbatch); reduction over K in slices of 32
 template <bool ACCUM, bool ELUAUX, bool BT>
 __global__ void __launch_bounds__(256) k_gemm_tf32_rows(const RowsBatch rb, const float* __restrict__ aux, long long M, int N, int K, int vecA, int vecB) {
-    __shared__ __align__(16) float As[2][16][LD];
-    __shared__ __align__(16) float Bs[2][16][LD];
+    constexpr int KS = 32;      // reduction slice: 64 x 32 of A (8 KB) + the B slice per CTA in flight while the previous one is multiplied
+    __shared__ __align__(16) float As[2][KS][LD];
+    __shared__ __align__(16) float Bs[2][KS][LD];
     const int z = blockIdx.z;   // selects instead of a dynamic index: the parameter struct stays in the constant bank
     const float* __restrict__ A = z == 0 ? rb.A[0] : (z == 1 ? rb.A[1] : rb.A[2]);
     const float* __restrict__ B = z == 0 ? rb.B[0] : (z == 1 ? rb.B[1] : rb.B[2]);
@@ -64,23 +65,30 @@ __global__ void __launch_bounds__(256) k_gemm_tf32_rows(const RowsBatch rb, cons
     const long long m0 = (long long)blockIdx.x * 64;
     const int n0 = blockIdx.y * 64;
     const int mrow = (warp & 3) * 16, ncol = (warp >> 2) * 32;
-    // A slice 64 rows x 16 k: thread -> (row tid/4, k (tid%4)*4);  B slice: [K][N] -> (k tid/16, n (tid%16)*4);  [N][K] -> like A
+    // A slice 64 rows x 32 k: thread -> (row tid/4, k (tid%4)*4 + 16 j);  B slice: [K][N] -> (k tid/16 + 16 j, n (tid%16)*4);  [N][K] -> like A
     const int arow = tid >> 2, ak = (tid & 3) * 4;
     const int bk = tid >> 4, bn = (tid & 15) * 4;
-    const int nsteps = (K + 15) / 16;
-    float4 ra, rbv;
+    const int nsteps = (K + KS - 1) / KS;
+    float4 ra[KS / 16], rbv[KS / 16];
     auto fetch = [&](int s) {
-        const int k0 = s * 16;
-        ra = ld4(A, m0 + arow, K, k0 + ak, K, m0 + arow < M, vecA);
-        if (BT) rbv = ld4(B, n0 + arow, K, k0 + ak, K, n0 + arow < N, vecB);
-        else rbv = ld4(B, k0 + bk, N, n0 + bn, N, k0 + bk < K, vecB);
+        const int k0 = s * KS;
+#pragma unroll
+        for (int j = 0; j < KS / 16; j++) {
+            ra[j] = ld4(A, m0 + arow, K, k0 + ak + 16 * j, K, m0 + arow < M, vecA);
+            if (BT) rbv[j] = ld4(B, n0 + arow, K, k0 + ak + 16 * j, K, n0 + arow < N, vecB);
+            else rbv[j] = ld4(B, k0 + bk + 16 * j, N, n0 + bn, N, k0 + bk + 16 * j < K, vecB);
+        }
     };
     auto stash = [&](int buf) {
-        As[buf][ak][arow] = tf32r(ra.x); As[buf][ak + 1][arow] = tf32r(ra.y); As[buf][ak + 2][arow] = tf32r(ra.z); As[buf][ak + 3][arow] = tf32r(ra.w);
-        if (BT) {
-            Bs[buf][ak][arow] = tf32r(rbv.x); Bs[buf][ak + 1][arow] = tf32r(rbv.y); Bs[buf][ak + 2][arow] = tf32r(rbv.z); Bs[buf][ak + 3][arow] = tf32r(rbv.w);
-        } else {
-            *reinterpret_cast<float4*>(&Bs[buf][bk][bn]) = make_float4(tf32r(rbv.x), tf32r(rbv.y), tf32r(rbv.z), tf32r(rbv.w));
+#pragma unroll
+        for (int j = 0; j < KS / 16; j++) {
+            const int kk = ak + 16 * j;
+            As[buf][kk][arow] = tf32r(ra[j].x); As[buf][kk + 1][arow] = tf32r(ra[j].y); As[buf][kk + 2][arow] = tf32r(ra[j].z); As[buf][kk + 3][arow] = tf32r(ra[j].w);
+            if (BT) {
+                Bs[buf][kk][arow] = tf32r(rbv[j].x); Bs[buf][kk + 1][arow] = tf32r(rbv[j].y); Bs[buf][kk + 2][arow] = tf32r(rbv[j].z); Bs[buf][kk + 3][arow] = tf32r(rbv[j].w);
+            } else {
+                *reinterpret_cast<float4*>(&Bs[buf][bk + 16 * j][bn]) = make_float4(tf32r(rbv[j].x), tf32r(rbv[j].y), tf32r(rbv[j].z), tf32r(rbv[j].w));
+            }
         }
     };
     float acc[4][4] = {};
@@ -90,8 +98,10 @@ __global__ void __launch_bounds__(256) k_gemm_tf32_rows(const RowsBatch rb, cons
     for (int s = 0; s < nsteps; s++) {
         const int buf = s & 1;
         if (s + 1 < nsteps) fetch(s + 1);
-        slice_mma(As[buf], Bs[buf], 0, mrow, ncol, gq, tq, acc);
-        slice_mma(As[buf], Bs[buf], 8, mrow, ncol, gq, tq, acc);
+        const int kleft = K - s * KS;      // skip the all-zero tail of the last slice
+#pragma unroll
+        for (int kk = 0; kk < KS; kk += 8)
+            if (kk < kleft) slice_mma(As[buf], Bs[buf], kk, mrow, ncol, gq, tq, acc);
         if (s + 1 < nsteps) stash(buf ^ 1);
         __syncthreads();
     }
@@ -107,8 +117,8 @@ __global__ void __launch_bounds__(256) k_gemm_tf32_rows(const RowsBatch rb, cons
             if (bias) { v0 += __ldg(bias + n); if (two) v1 += __ldg(bias + n + 1); }
             if (ELUAUX) {
                 const float x0 = aux[m * N + n];
-                v0 *= x0 > 0.f ? 1.f : expf(x0);
-                if (two) { const float x1 = aux[m * N + n + 1]; v1 *= x1 > 0.f ? 1.f : expf(x1); }
+                v0 *= x0 > 0.f ? 1.f : __expf(x0);
+                if (two) { const float x1 = aux[m * N + n + 1]; v1 *= x1 > 0.f ? 1.f : __expf(x1); }
             }
             float* dst = C + m * N + n;
             if (ACCUM) { v0 += dst[0]; if (two) v1 += dst[1]; }
@@ -137,7 +147,8 @@ __global__ void __launch_bounds__(256) k_gemm_tf32_wgrad(const float* __restrict
         a0 = ld4(A, r + lr, K, k0 + lc, K, r + lr < r1, vecA);
         a1 = ld4(A, r + lr + 16, K, k0 + lc, K, r + lr + 16 < r1, vecA);
     };
-    auto f = [](float v) { return tf32r(ELU_A ? elu1(v) : v); };
+    // ELU through the fast exponential: its absolute error (1e-7) is far below the tf32 rounding applied next
+    auto f = [](float v) { return tf32r(ELU_A ? (v > 0.f ? v : __expf(v) - 1.f) : v); };
     auto stash = [&](int buf) {
         *reinterpret_cast<float4*>(&Gs[buf][lr][lc]) = make_float4(tf32r(g0.x), tf32r(g0.y), tf32r(g0.z), tf32r(g0.w));
         *reinterpret_cast<float4*>(&Gs[buf][lr + 16][lc]) = make_float4(tf32r(g1.x), tf32r(g1.y), tf32r(g1.z), tf32r(g1.w));

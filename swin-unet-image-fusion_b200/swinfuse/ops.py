@@ -392,6 +392,19 @@ _WA_TENSORS = ("ln_q_gamma", "ln_q_beta", "ln_kv_gamma", "ln_kv_beta", "wq", "bq
                "bias_table")
 
 
+def _zero_grads_like(tens):
+    """One zero-filled flat buffer carved into views shaped like `tens` (None stays None): the backward kernels
+    accumulate parameter gradients into caller-zeroed memory, and one fill replaces a dozen tiny ones per operator."""
+    offs, total = [], 0
+    for t in tens:
+        offs.append(total)
+        if t is not None:
+            total += (t.numel() + 63) // 64 * 64      # every view starts on a 256-byte boundary
+    like = next(t for t in tens if t is not None)
+    flat = torch.zeros(total, dtype=torch.float32, device=like.device)
+    return [None if t is None else flat[o:o + t.numel()].view(t.shape) for t, o in zip(tens, offs)]
+
+
 def _fill_wa(p: _lib.WindowAttnParams, q, kv, residual, out, tensors, cfg) -> None:
     nh, d, wsh, wsw, shift, eps, prec = cfg
     b, c, h, w = q.shape
@@ -438,7 +451,7 @@ class _WindowAttn(torch.autograd.Function):
         _fill_wa(p.fwd, q, kv_t, None, dummy_out, tens, ctx.cfg)
         gq = torch.empty_like(q)
         gkv = None if ctx.self_attn else torch.empty_like(kv_t)
-        grads = [None if t is None else torch.zeros_like(t) for t in tens]
+        grads = _zero_grads_like(tens)
         p.gout, p.g_q_src, p.g_kv_src = gout.data_ptr(), gq.data_ptr(), _ptr(gkv)
         for name, g in zip(_WA_TENSORS, grads):
             setattr(p, "g_" + name, _ptr(g))
@@ -518,7 +531,7 @@ class _Mlp(torch.autograd.Function):
         p = _lib.MlpBwdParams()
         _fill_mlp(p.fwd, x, None, gout, tens, eps, prec)
         gin = torch.empty_like(x)
-        grads = [None if t is None else torch.zeros_like(t) for t in tens]
+        grads = _zero_grads_like(tens)
         p.gout, p.g_in = gout.data_ptr(), gin.data_ptr()
         for name, g in zip(_MLP_TENSORS, grads):
             setattr(p, "g_" + name, _ptr(g))

@@ -224,7 +224,7 @@ def test_bf16_mode_gradients_track_the_fp32_ones():
     assert worst[0] <= 1.5e-1, worst
 
 
-@pytest.mark.parametrize("c,nh,d", [(24, 8, 3), (48, 8, 6), (96, 8, 12)])
+@pytest.mark.parametrize("c,nh,d", [(24, 8, 3), (48, 8, 6), (96, 8, 12), (192, 8, 24), (384, 8, 48)])
 @pytest.mark.parametrize("shifted", [False, True])
 @pytest.mark.parametrize("cross", [False, True])
 def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted, cross):
@@ -239,8 +239,10 @@ def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted
                          use_cross_attention=cross, use_qkv_bias=True, attention_drop_ratio=0.0,
                          linear_after_att_drop_ratio=0.0)
     with torch.no_grad():
-        for prm in wa.parameters():
-            prm.copy_(torch.randn(prm.shape, generator=gen) * (0.3 if prm.dim() > 1 else 0.1))
+        for name, prm in wa.named_parameters():
+            # projection weights at the kaiming scale a016 initialises them with (scores of order one), table and biases small
+            std = 0.3 if "table" in name else (c ** -0.5 if prm.dim() > 1 else 0.1)
+            prm.copy_(torch.randn(prm.shape, generator=gen) * std)
     wa = wa.cuda()
     q0 = torch.randn(2, c, 21, 28, generator=gen)
     kv0 = torch.randn(2, c, 21, 28, generator=gen)
