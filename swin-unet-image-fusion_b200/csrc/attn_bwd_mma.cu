@@ -53,6 +53,11 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float quad_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
     return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -105,7 +110,8 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(co
     }
     ws->reg2[0][threadIdx.x & 63] = 0;
     ws->reg2[1][threadIdx.x & 63] = 0;
-    for (int i = threadIdx.x; i < 169; i += WARPS * 32) { ws->tab[i] = table[i]; ws->gtab[i] = 0.f; }
+    for (int i = threadIdx.x; i < 169; i += WARPS * 32) { ws->tab[i] = table[i] * LOG2E; ws->gtab[i] = 0.f; }
+    const float scale_l2 = scale * LOG2E;
     const int gq = lane >> 2, tq = lane & 3;
     const int r0 = 16 * m + gq, r1 = r0 + 8;
     // rows >= 49 are computed on clamped indices and zeroed
@@ -214,30 +220,39 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(co
         }
         // ---- softmax rows r0 (c = 0,1) and r1 (c = 2,3)
         const uint32_t rr0 = (uint32_t)reg[rc0], rr1 = (uint32_t)reg[rc1];
+        // logits in the log2 domain: (raw * scale + bias) * log2(e), bias table pre-multiplied in shared memory
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int n = 0; n < 7; n++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const bool jv = 8 * n + 2 * tq + e < T;
-                float s0 = fmaf(s[n][e], scale, ws->tab[qo0 + cj[n][e]]), s1 = fmaf(s[n][2 + e], scale, ws->tab[qo1 + cj[n][e]]);
-                if (has_mask) {
-                    const uint32_t cr = ((n < 4 ? creg0 >> (4 * (2 * n + e)) : creg1 >> (4 * (2 * (n - 4) + e))) & 15u);
-                    if (cr != rr0) s0 = -1e10f;
-                    if (cr != rr1) s1 = -1e10f;
-                }
-                s0 = jv ? s0 : -INFINITY;
-                s1 = jv ? s1 : -INFINITY;
-                s[n][e] = s0; s[n][2 + e] = s1;
-                mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
+                s[n][e] = fmaf(s[n][e], scale_l2, ws->tab[qo0 + cj[n][e]]);
+                s[n][2 + e] = fmaf(s[n][2 + e], scale_l2, ws->tab[qo1 + cj[n][e]]);
             }
+        if (has_mask) {      // CTA-uniform: only windows on the shifted frame's seams carry more than one region
+#pragma unroll
+            for (int n = 0; n < 7; n++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const uint32_t cr = ((n < 4 ? creg0 >> (4 * (2 * n + e)) : creg1 >> (4 * (2 * (n - 4) + e))) & 15u);
+                    if (cr != rr0) s[n][e] = -1e10f;
+                    if (cr != rr1) s[n][2 + e] = -1e10f;
+                }
+        }
+        // key columns 49..55 exist only in tile 6 (its lanes with 2 tq + e >= 1)
+        if (tq != 0) { s[6][0] = -INFINITY; s[6][2] = -INFINITY; }
+        s[6][1] = -INFINITY; s[6][3] = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < 7; n++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) { mx0 = fmaxf(mx0, s[n][e]); mx1 = fmaxf(mx1, s[n][2 + e]); }
         mx0 = quad_max(mx0); mx1 = quad_max(mx1);
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int n = 0; n < 7; n++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const float e0 = exp2f((s[n][e] - mx0) * LOG2E), e1 = exp2f((s[n][2 + e] - mx1) * LOG2E);
+                const float e0 = ex2_approx(s[n][e] - mx0), e1 = ex2_approx(s[n][2 + e] - mx1);
                 s[n][e] = e0; s[n][2 + e] = e1;
                 sum0 += e0; sum1 += e1;
             }

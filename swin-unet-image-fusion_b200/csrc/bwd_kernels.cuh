@@ -20,5 +20,5 @@ int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, con
 struct GemmBatch;
 int gemm_tf32_nn(const float* A, const float* B, const float* aux, float* C, long long M, int N, int K, bool accum, cudaStream_t st);
 int gemm_tf32_nt(const GemmBatch& batch, int nbatch, long long M, int N, int K, cudaStream_t st);
-int gemm_tf32_wgrad(const float* G, const float* A, float* Wg, long long M, int N, int K, bool elu_a, cudaStream_t st);
+int gemm_tf32_wgrad(const float* G, const float* A, float* Wg, float* bias_grad, long long M, int N, int K, bool elu_a, cudaStream_t st);
 }  // namespace sf

@@ -139,10 +139,13 @@ __global__ void __launch_bounds__(256) k_gemm_tn_reduce(const float* __restrict_
     }
 }
 
+static int launch_colsum(const float* G, float* out, long long M, int N, cudaStream_t st);
+// bias_grad (optional): += column sums of G -- fused into the tensor-core kernel, a separate pass for the exact fp32 one
 static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long long M, int N, int K, bool elu_a, cudaStream_t st,
-                                 bool tf32 = false) {
+                                 bool tf32 = false, float* bias_grad = nullptr) {
+    if (tf32 && Wg) return gemm_tf32_wgrad(G, A, Wg, bias_grad, M, N, K, elu_a, st);
+    if (bias_grad) SF_TRY(launch_colsum(G, bias_grad, M, N, st));
     if (!Wg) return SF_OK;
-    if (tf32) return gemm_tf32_wgrad(G, A, Wg, M, N, K, elu_a, st);
     const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
     long long splits = (148LL * 4 + tiles - 1) / tiles;
     long long max_splits = (M + 255) / 256;
@@ -714,19 +717,15 @@ int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws
     const bool fused_o = tf && attn_core_bwd_mma_supported(geom, p->head_dim);
     if (!fused_o) SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
     // ---- output projection: gradient w.r.t. O -----------------------------------------------------------
-    SF_TRY(launch_colsum(bp->gout, bp->g_bo, M, C, st));
     SF_TRY(launch_gemm_nn(bp->gout, p->wo, nullptr, gO, M, inner, C, false, st, tf));
     // ---- attention core ---------------------------------------------------------------------------------
     SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, tf,
                                 fused_o ? O : nullptr));
-    SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st, tf));
+    SF_TRY(launch_gemm_tn_reduce(bp->gout, O, bp->g_wo, M, C, inner, false, st, tf, bp->g_bo));
     // ---- projections --------------------------------------------------------------------------------------
-    SF_TRY(launch_colsum(dQ, bp->g_bq, M, inner, st));
-    SF_TRY(launch_colsum(dK, bp->g_bk, M, inner, st));
-    SF_TRY(launch_colsum(dV, bp->g_bv, M, inner, st));
-    SF_TRY(launch_gemm_tn_reduce(dQ, nq, bp->g_wq, M, inner, C, false, st, tf));
-    SF_TRY(launch_gemm_tn_reduce(dK, nkv, bp->g_wk, M, inner, C, false, st, tf));
-    SF_TRY(launch_gemm_tn_reduce(dV, nkv, bp->g_wv, M, inner, C, false, st, tf));
+    SF_TRY(launch_gemm_tn_reduce(dQ, nq, bp->g_wq, M, inner, C, false, st, tf, bp->g_bq));
+    SF_TRY(launch_gemm_tn_reduce(dK, nkv, bp->g_wk, M, inner, C, false, st, tf, bp->g_bk));
+    SF_TRY(launch_gemm_tn_reduce(dV, nkv, bp->g_wv, M, inner, C, false, st, tf, bp->g_bv));
     // gradients w.r.t. the (normalised) operands
     float* gq_dst = need_q ? gnq : bp->g_q_src;
     SF_TRY(launch_gemm_nn(dQ, p->wq, nullptr, gq_dst, M, C, inner, false, st, tf));
@@ -778,11 +777,9 @@ int mlp_bwd(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStre
     GemmBatch g1{};
     g1.p[0] = GemmProblem{n, p->w1, p->b1, nullptr, hpre};
     SF_TRY(tf ? gemm_tf32_nt(g1, 1, M, H, C, st) : launch_gemm_tn(g1, 1, M, H, C, false, st));
-    SF_TRY(launch_colsum(bp->gout, bp->g_b2, M, C, st));
-    SF_TRY(launch_gemm_tn_reduce(bp->gout, hpre, bp->g_w2, M, C, H, true, st, tf));      // gW2 = gout^T ELU(hpre)
+    SF_TRY(launch_gemm_tn_reduce(bp->gout, hpre, bp->g_w2, M, C, H, true, st, tf, bp->g_b2));      // gW2 = gout^T ELU(hpre), gb2
     SF_TRY(launch_gemm_nn(bp->gout, p->w2, hpre, gh, M, H, C, false, st, tf));           // g_hpre = (gout W2) o ELU'(hpre)
-    SF_TRY(launch_colsum(gh, bp->g_b1, M, H, st));
-    SF_TRY(launch_gemm_tn_reduce(gh, n, bp->g_w1, M, H, C, false, st, tf));
+    SF_TRY(launch_gemm_tn_reduce(gh, n, bp->g_w1, M, H, C, false, st, tf, bp->g_b1));
     float* gdst = p->ln_gamma ? gn : bp->g_in;
     SF_TRY(launch_gemm_nn(gh, p->w1, nullptr, gdst, M, C, H, false, st, tf));
     if (p->ln_gamma) SF_TRY(launch_ln_bwd(p->in, p->ln_gamma, p->ln_beta, gn, bp->g_in, bp->g_ln_gamma, bp->g_ln_beta, M, C, p->ln_eps, false, false, st));
@@ -822,8 +819,7 @@ int patch_bwd(const sf_patch_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cuda
     const float* gy = bp->gout;
     if (!p->encoder) { SF_TRY(sf_patch_merge(bp->gout, gpost, p->B, p->H * p->mh, p->W * p->mw, p->Cout, p->mh, p->mw, (void*)st)); gy = gpost; }
     SF_TRY(launch_ln_bwd(lin, p->ln_gamma, p->ln_beta, gy, glin, bp->g_ln_gamma, bp->g_ln_beta, Mr, N, p->ln_eps, true, false, st));
-    SF_TRY(launch_colsum(glin, bp->g_b, Mr, N, st));
-    SF_TRY(launch_gemm_tn_reduce(glin, A, bp->g_w, Mr, N, K, false, st, tf));
+    SF_TRY(launch_gemm_tn_reduce(glin, A, bp->g_w, Mr, N, K, false, st, tf, bp->g_b));
     if (p->encoder) {
         SF_TRY(launch_gemm_nn(glin, p->w, nullptr, gA, Mr, K, N, false, st, tf));
         SF_TRY(sf_patch_unmerge(gA, bp->g_in, p->B, p->H / p->mh, p->W / p->mw, p->Cin, p->mh, p->mw, (void*)st));

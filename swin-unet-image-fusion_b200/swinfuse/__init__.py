@@ -16,7 +16,7 @@ from .ops import get_default_precision, set_default_precision  # noqa: F401
 DROPIN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin")
 
 _DROPIN_MODULES = ("a001_WindowAttention", "a002_AutoPathWinAtt", "a003_AutoPathMLP",
-                   "a004_AddAndLayerNormWithOtherModule", "a005_BasicBlock", "a006_PaddingOperation", "a007_utils",
+                   "a004_AddAndLayerNormWithOtherModule", "a005_BasicBlock", "a006_PaddingOperation", "a007_utils", "a008_loss",
                    "a009_NormalAndShiftWinsBlockPair", "a010_StateRecorder", "a011_PatchOperation",
                    "a012_SelfAndCrossBlockPair", "a013_ModelDefinition")
 

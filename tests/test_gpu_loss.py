@@ -74,3 +74,26 @@ def test_fusion_loss_rejects_cpu_tensors():
     x = torch.rand(1, 1, 32, 32)
     with pytest.raises(SwinFuseError):
         FusionLoss()(x, x, x)
+
+
+def test_dropin_myloss_matches_the_restatement_and_keeps_the_a008_bookkeeping():
+    """dropin/a008_loss.py: MyLoss.calcu_total_loss returns (tensor, dict rounded to 5 digits) like a008:226-282 and
+    the history means of a008:284-311."""
+    import swinfuse
+    swinfuse.install_dropin()
+    import importlib
+    import a008_loss
+    importlib.reload(a008_loss)
+    g = torch.Generator().manual_seed(3)
+    x, ir, vis = (torch.rand(2, 1, 40, 72, generator=g) for _ in range(3))
+    ref_total, ref_terms, ref_g = _oracle(x, ir, vis, False)
+    loss = a008_loss.MyLoss().cuda()
+    xd = x.cuda().requires_grad_(True)
+    total, d = loss.calcu_total_loss(xd, ir.cuda(), vis.cuda())
+    total.backward()
+    assert abs(float(total.detach()) - float(ref_total)) <= TOL * abs(float(ref_total))
+    assert float((xd.grad.cpu() - ref_g).abs().max()) <= TOL * float(ref_g.abs().max())
+    assert set(d) == {"ssim_loss", "texture_loss", "intensity_loss", "psnr_loss", "total_loss"}
+    assert abs(d["ssim_loss"] - float(ref_terms[1])) <= 2e-4 * abs(float(ref_terms[1])) + 1e-5
+    means = loss.calcu_history_mean_and_clear_and_save_to_mean_recorder()
+    assert means["total_loss_mean"] == d["total_loss"] and not loss.loss_recorder_in_detail.record_stack
