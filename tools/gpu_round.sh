@@ -12,6 +12,8 @@ if [ "$2" = "full" ]; then
 fi
 timeout 600 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err || tail -5 $out/${tag}_bench.err
 python tools/summarize_bench.py $out/${tag}_bench.json | cut -c1-150 | head -30
+timeout 600 python bench.py --mode train --steps 6 --warmup 3 > $out/${tag}_train_1gpu.json 2> $out/${tag}_train_1gpu.err || tail -5 $out/${tag}_train_1gpu.err
+python -c "import json,sys; d=json.load(open('$out/${tag}_train_1gpu.json')); print('train', round(d['value'],1), d['unit'], round(d['ms_per_step'],2), 'ms/step', 'loss', d['loss_first'], '->', d['loss_last'])"
 if [ "$2" = "full" ]; then
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_reference_arm.json 2> $out/${tag}_reference_arm.err
   cat $out/${tag}_reference_arm.json | cut -c1-400
