@@ -410,7 +410,7 @@ def run_train(args, rank: int, world: int, local_rank: int):
                sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}
     line = {"metric": "training image pairs/sec", "value": pairs / (ms / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "steps_per_s": args.steps / (ms / 1e3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision + " fwd / fp32 bwd",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision + " fwd / tf32 + fp16 tensor-core bwd, fp32 accumulation",
             "data": "synthetic",
             "config": {"workload": f"training step B={B}/GPU {S}x{S} pairs, data parallel (BASELINE configs[2])",
                        "global_batch": B * world, "loss": "a008 loss + gradient in libswinfuse kernels (sf_fusion_loss: separable MS-SSIM+L1, Sobel, intensity; clamp folded in)",

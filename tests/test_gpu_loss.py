@@ -5,6 +5,7 @@ sum 33-tap windows in a different order than the dense 33x33 convolution and use
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -97,3 +98,52 @@ def test_dropin_myloss_matches_the_restatement_and_keeps_the_a008_bookkeeping():
     assert abs(d["ssim_loss"] - float(ref_terms[1])) <= 2e-4 * abs(float(ref_terms[1])) + 1e-5
     means = loss.calcu_history_mean_and_clear_and_save_to_mean_recorder()
     assert means["total_loss_mean"] == d["total_loss"] and not loss.loss_recorder_in_detail.record_stack
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_a016_training_loop_body_with_the_dropin_model_and_loss(precision):
+    """The body of a016's training loop (a016:150-165) on the drop-in modules only: MyModel (kwargs of a016:26-40,
+    init_params of a016:382-390) -> torch.clamp_ -> MyLoss.calcu_total_loss -> zero_grad / backward / torch.optim.Adam.step.
+    The loss on a fixed batch must fall and the first step must agree between the fp32 and bf16 operator modes."""
+    from torch import nn
+    from oracle.make_golden import small_cfg
+    from tests.util import build_model, dropin
+    sw = dropin()
+    import importlib
+    import a008_loss
+    importlib.reload(a008_loss)
+    sw.set_default_precision(precision)
+    try:
+        torch.manual_seed(0)
+        model = build_model(small_cfg(), act=nn.ELU()).train()
+
+        def init_params(m):   # a016:382-390
+            if isinstance(m, (nn.Linear, nn.Conv2d)):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        model.apply(init_params)
+        loss_fn = a008_loss.MyLoss().cuda()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        g = torch.Generator().manual_seed(9)
+        ir, vis = torch.rand(2, 1, 64, 64, generator=g).cuda(), torch.rand(2, 1, 64, 64, generator=g).cuda()
+        hist = []
+        for _ in range(6):
+            fusion = model(ir, vis)
+            fusion = torch.clamp_(fusion, min=0, max=1)
+            loss, detail = loss_fn.calcu_total_loss(fusion_images=fusion, ir_images=ir, vis_images=vis)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            hist.append(detail["total_loss"])
+        assert all(np.isfinite(hist)), hist
+        assert hist[-1] < hist[0], hist
+        test_a016_training_loop_body_with_the_dropin_model_and_loss.first[precision] = hist[0]
+        first = test_a016_training_loop_body_with_the_dropin_model_and_loss.first
+        if len(first) == 2:
+            assert abs(first["bf16"] - first["fp32"]) <= 2e-2 * abs(first["fp32"]), first
+    finally:
+        sw.set_default_precision("fp32")
+
+
+test_a016_training_loop_body_with_the_dropin_model_and_loss.first = {}
