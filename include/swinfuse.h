@@ -173,6 +173,8 @@ typedef struct {
     float* g_ln_kv_gamma; float* g_ln_kv_beta;
     float* g_wq; float* g_bq; float* g_wk; float* g_bk; float* g_wv; float* g_bv; float* g_wo; float* g_bo;
     float* g_bias_table;
+    const float* add_to_g_q_src;  /* optional (B,Hp,Wp,C): added to g_q_src -- pass gout when fwd.residual was q_src itself
+                                     (x + Attn(LN(x)), a004:29-38), so the two gradient branches of x leave as one tensor */
 } sf_window_attn_bwd_params;
 size_t sf_window_attn_bwd_workspace_bytes(const sf_window_attn_bwd_params* p);
 int sf_window_attn_bwd(const sf_window_attn_bwd_params* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -203,6 +205,7 @@ typedef struct {
     float* g_in;
     float* g_ln_gamma; float* g_ln_beta;
     float* g_w1; float* g_b1; float* g_w2; float* g_b2;
+    const float* add_to_g_in;     /* optional (M,C): added to g_in (gout when fwd.residual was the input itself) */
 } sf_mlp_bwd_params;
 size_t sf_mlp_bwd_workspace_bytes(const sf_mlp_bwd_params* p);
 int sf_mlp_bwd(const sf_mlp_bwd_params* p, void* workspace, size_t workspace_bytes, void* stream);

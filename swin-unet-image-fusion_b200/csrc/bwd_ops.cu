@@ -226,7 +226,7 @@ static int launch_colsum(const float* G, float* out, long long M, int N, cudaStr
 // =============================================================================================
 template <bool ELUOUT, bool ACCUM>
 __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                         const float* __restrict__ gy, float* __restrict__ gx, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                         const float* __restrict__ gy, float* gx, const float* gadd, float* __restrict__ ggamma, float* __restrict__ gbeta,
                          long long M, int C, float eps) {
     // per-warp private [2][C] accumulators: lane l owns columns l, l+32, ... of its warp's copy, so the updates need
     // neither atomics nor synchronisation; the copies are summed once at the end
@@ -266,7 +266,7 @@ __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ 
             float g = gr[c];
             if (ELUOUT) g *= elu_grad(xh * gamma[c] + beta[c]);
             float val = rstd * (g * gamma[c] - s1 - xh * s2);
-            if (ACCUM) val += gx[row * C + c];
+            if (ACCUM) val += gadd[row * C + c];
             gx[row * C + c] = val;
         }
     }
@@ -285,7 +285,7 @@ __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ 
 // lane's channels never change: ggamma / gbeta partial sums stay in eight registers until the end of the kernel.
 template <int G, bool ELUOUT, bool ACCUM>
 __global__ void __launch_bounds__(256) k_ln_bwd_grp(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                    const float* __restrict__ gy, float* __restrict__ gx, float* __restrict__ ggamma,
+                                                    const float* __restrict__ gy, float* gx, const float* gadd, float* __restrict__ ggamma,
                                                     float* __restrict__ gbeta, long long M, int C, float eps) {
     __shared__ float sacc[8][2][128];
     constexpr int RPW = 32 / G;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) k_ln_bwd_grp(const float* __restrict__ x,
         if (ok) {
             float4 o4 = make_float4(rstd * (g0 - s1 - h0 * s2), rstd * (g1 - s1 - h1 * s2), rstd * (g2 - s1 - h2 * s2), rstd * (g3 - s1 - h3 * s2));
             float4* dst = reinterpret_cast<float4*>(gx + row * C + c0);
-            if (ACCUM) { const float4 old = *dst; o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w; }
+            if (ACCUM) { const float4 old = *reinterpret_cast<const float4*>(gadd + row * C + c0); o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w; }
             *dst = o4;
             ag[0] = fmaf(gv.x, h0, ag[0]); ag[1] = fmaf(gv.y, h1, ag[1]); ag[2] = fmaf(gv.z, h2, ag[2]); ag[3] = fmaf(gv.w, h3, ag[3]);
             ab[0] += gv.x; ab[1] += gv.y; ab[2] += gv.z; ab[3] += gv.w;
@@ -358,29 +358,32 @@ __global__ void __launch_bounds__(256) k_ln_bwd_grp(const float* __restrict__ x,
 }
 
 template <int G>
-static void launch_ln_bwd_grp(const float* x, const float* gamma, const float* beta, const float* gy, float* gx, float* ggamma, float* gbeta,
-                              long long M, int C, float eps, bool eluout, bool accum, cudaStream_t st) {
+static void launch_ln_bwd_grp(const float* x, const float* gamma, const float* beta, const float* gy, float* gx, const float* gadd, float* ggamma,
+                              float* gbeta, long long M, int C, float eps, bool eluout, cudaStream_t st) {
+    const bool accum = gadd != nullptr;
     const long long rows_per_block = 8 * (32 / G);
     long long blocks = (M + rows_per_block - 1) / rows_per_block;
     if (blocks > 148LL * 8) blocks = 148LL * 8;
     if (eluout) {
-        if (accum) k_ln_bwd_grp<G, true, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
-        else k_ln_bwd_grp<G, true, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        if (accum) k_ln_bwd_grp<G, true, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd_grp<G, true, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
     } else {
-        if (accum) k_ln_bwd_grp<G, false, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
-        else k_ln_bwd_grp<G, false, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        if (accum) k_ln_bwd_grp<G, false, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd_grp<G, false, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
     }
 }
 
+// gadd (optional): a (M,C) tensor added to the result -- gx itself to accumulate in place, or another gradient branch
 static int launch_ln_bwd(const float* x, const float* gamma, const float* beta, const float* gy, float* gx, float* ggamma,
-                         float* gbeta, long long M, int C, float eps, bool eluout, bool accum, cudaStream_t st) {
+                         float* gbeta, long long M, int C, float eps, bool eluout, const float* gadd, cudaStream_t st) {
+    const bool accum = gadd != nullptr;
     const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx) |
-                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(gadd)) & 15) == 0;
     if (C <= 128 && (C & 3) == 0 && al16) {
         ProfScope ps("bwd_layernorm", 20.0 * (double)M * C, 12.0 * (double)M * C, st);
-        if (C <= 32) launch_ln_bwd_grp<8>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps, eluout, accum, st);
-        else if (C <= 64) launch_ln_bwd_grp<16>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps, eluout, accum, st);
-        else launch_ln_bwd_grp<32>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps, eluout, accum, st);
+        if (C <= 32) launch_ln_bwd_grp<8>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps, eluout, st);
+        else if (C <= 64) launch_ln_bwd_grp<16>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps, eluout, st);
+        else launch_ln_bwd_grp<32>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps, eluout, st);
         SF_CHECK_LAUNCH("bwd_layernorm");
         return SF_OK;
     }
@@ -402,11 +405,11 @@ static int launch_ln_bwd(const float* x, const float* gamma, const float* beta, 
     }
     ProfScope ps("bwd_layernorm", 20.0 * (double)M * C, 12.0 * (double)M * C, st);
     if (eluout) {
-        if (accum) k_ln_bwd<true, true><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
-        else k_ln_bwd<true, false><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        if (accum) k_ln_bwd<true, true><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd<true, false><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
     } else {
-        if (accum) k_ln_bwd<false, true><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
-        else k_ln_bwd<false, false><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, ggamma, gbeta, M, C, eps);
+        if (accum) k_ln_bwd<false, true><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
+        else k_ln_bwd<false, false><<<(unsigned)blocks, threads, smem, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
     }
     SF_CHECK_LAUNCH("bwd_layernorm");
     return SF_OK;
@@ -739,13 +742,15 @@ int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws
         SF_TRY(launch_gemm_nn(dV, p->wv, nullptr, gkv_dst, M, C, inner, true, st, tf));
     }
     // ---- LayerNorm adjoints -----------------------------------------------------------------------------
-    if (need_q) SF_TRY(launch_ln_bwd(p->q_src, p->ln_q_gamma, p->ln_q_beta, gnq, bp->g_q_src, bp->g_ln_q_gamma, bp->g_ln_q_beta, M, C, p->ln_eps, false, false, st));
+    // add_to_g_q_src: the residual branch's gradient rides along instead of a separate add kernel
+    if (need_q) SF_TRY(launch_ln_bwd(p->q_src, p->ln_q_gamma, p->ln_q_beta, gnq, bp->g_q_src, bp->g_ln_q_gamma, bp->g_ln_q_beta, M, C, p->ln_eps, false, bp->add_to_g_q_src, st));
+    else if (bp->add_to_g_q_src) SF_TRY(sf_add(bp->g_q_src, bp->add_to_g_q_src, bp->g_q_src, M * C, (void*)st));
     if (!share) {
         // where does the kv-side gradient land?  g_kv_src if given, else (same source tensor) it is added to g_q_src
         float* dst = bp->g_kv_src ? bp->g_kv_src : bp->g_q_src;
         const bool accum = bp->g_kv_src == nullptr;
         if (need_kv) {
-            SF_TRY(launch_ln_bwd(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, gnkv, dst, bp->g_ln_kv_gamma, bp->g_ln_kv_beta, M, C, p->ln_eps, false, accum, st));
+            SF_TRY(launch_ln_bwd(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, gnkv, dst, bp->g_ln_kv_gamma, bp->g_ln_kv_beta, M, C, p->ln_eps, false, accum ? dst : nullptr, st));
         } else if (accum) {
             SF_TRY(sf_add(bp->g_q_src, gnkv, bp->g_q_src, M * C, (void*)st));
         }
@@ -782,7 +787,8 @@ int mlp_bwd(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStre
     SF_TRY(launch_gemm_tn_reduce(gh, n, bp->g_w1, M, H, C, false, st, tf, bp->g_b1));
     float* gdst = p->ln_gamma ? gn : bp->g_in;
     SF_TRY(launch_gemm_nn(gh, p->w1, nullptr, gdst, M, C, H, false, st, tf));
-    if (p->ln_gamma) SF_TRY(launch_ln_bwd(p->in, p->ln_gamma, p->ln_beta, gn, bp->g_in, bp->g_ln_gamma, bp->g_ln_beta, M, C, p->ln_eps, false, false, st));
+    if (p->ln_gamma) SF_TRY(launch_ln_bwd(p->in, p->ln_gamma, p->ln_beta, gn, bp->g_in, bp->g_ln_gamma, bp->g_ln_beta, M, C, p->ln_eps, false, bp->add_to_g_in, st));
+    else if (bp->add_to_g_in) SF_TRY(sf_add(bp->g_in, bp->add_to_g_in, bp->g_in, M * C, (void*)st));
     return SF_OK;
 }
 
@@ -818,7 +824,7 @@ int patch_bwd(const sf_patch_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cuda
     // gradient w.r.t. the LayerNorm output rows (ELU' is applied inside the LN backward kernel)
     const float* gy = bp->gout;
     if (!p->encoder) { SF_TRY(sf_patch_merge(bp->gout, gpost, p->B, p->H * p->mh, p->W * p->mw, p->Cout, p->mh, p->mw, (void*)st)); gy = gpost; }
-    SF_TRY(launch_ln_bwd(lin, p->ln_gamma, p->ln_beta, gy, glin, bp->g_ln_gamma, bp->g_ln_beta, Mr, N, p->ln_eps, true, false, st));
+    SF_TRY(launch_ln_bwd(lin, p->ln_gamma, p->ln_beta, gy, glin, bp->g_ln_gamma, bp->g_ln_beta, Mr, N, p->ln_eps, true, nullptr, st));
     SF_TRY(launch_gemm_tn_reduce(glin, A, bp->g_w, Mr, N, K, false, st, tf, bp->g_b));
     if (p->encoder) {
         SF_TRY(launch_gemm_nn(glin, p->w, nullptr, gA, Mr, K, N, false, st, tf));

@@ -33,7 +33,7 @@ class WindowAttnParams(C.Structure):
 class WindowAttnBwdParams(C.Structure):
     _fields_ = [("fwd", WindowAttnParams)] + [(n, _f) for n in (
         "gout", "g_q_src", "g_kv_src", "g_ln_q_gamma", "g_ln_q_beta", "g_ln_kv_gamma", "g_ln_kv_beta",
-        "g_wq", "g_bq", "g_wk", "g_bk", "g_wv", "g_bv", "g_wo", "g_bo", "g_bias_table")]
+        "g_wq", "g_bq", "g_wk", "g_bk", "g_wv", "g_bv", "g_wo", "g_bo", "g_bias_table", "add_to_g_q_src")]
 
 
 class MlpParams(C.Structure):
@@ -44,7 +44,7 @@ class MlpParams(C.Structure):
 
 class MlpBwdParams(C.Structure):
     _fields_ = [("fwd", MlpParams)] + [(n, _f) for n in (
-        "gout", "g_in", "g_ln_gamma", "g_ln_beta", "g_w1", "g_b1", "g_w2", "g_b2")]
+        "gout", "g_in", "g_ln_gamma", "g_ln_beta", "g_w1", "g_b1", "g_w2", "g_b2", "add_to_g_in")]
 
 
 class PatchParams(C.Structure):

@@ -392,17 +392,42 @@ _WA_TENSORS = ("ln_q_gamma", "ln_q_beta", "ln_kv_gamma", "ln_kv_beta", "wq", "bq
                "bias_table")
 
 
-def _zero_grads_like(tens):
-    """One zero-filled flat buffer carved into views shaped like `tens` (None stays None): the backward kernels
-    accumulate parameter gradients into caller-zeroed memory, and one fill replaces a dozen tiny ones per operator."""
-    offs, total = [], 0
-    for t in tens:
-        offs.append(total)
-        if t is not None:
+_direct_param_grads = False
+
+
+def set_direct_param_grads(on: bool) -> None:
+    """Let the backward kernels accumulate parameter gradients straight into ``param.grad`` (they add into their
+    destination with atomics anyway) instead of returning fresh tensors for autograd to add.  Only parameters whose
+    ``.grad`` already exists as a contiguous fp32 CUDA tensor take this route -- swinfuse.train.FlatParameters keeps
+    every ``.grad`` as a zero-initialised view of its flat gradient buffer, which removes ~1.4k tiny accumulation kernels
+    per training step.  Tensor hooks on such parameters do not fire (off by default; plain autograd semantics then)."""
+    global _direct_param_grads
+    _direct_param_grads = bool(on)
+
+
+def _param_grad_buffers(saved, tens):
+    """-> (buffers the kernels accumulate into, what backward() returns for them).
+
+    One zero-filled flat buffer carved into views shaped like `tens` (None stays None) -- one fill instead of a dozen
+    tiny ones per operator; with set_direct_param_grads(True) parameters that already own a .grad use it directly
+    (and backward() returns None for them)."""
+    bufs, rets = [None] * len(tens), [None] * len(tens)
+    offs, total = {}, 0
+    for i, (s, t) in enumerate(zip(saved, tens)):
+        if t is None:
+            continue
+        g = getattr(s, "grad", None) if _direct_param_grads else None
+        if g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.shape == t.shape:
+            bufs[i] = g
+        else:
+            offs[i] = total
             total += (t.numel() + 63) // 64 * 64      # every view starts on a 256-byte boundary
-    like = next(t for t in tens if t is not None)
-    flat = torch.zeros(total, dtype=torch.float32, device=like.device)
-    return [None if t is None else flat[o:o + t.numel()].view(t.shape) for t, o in zip(tens, offs)]
+    if offs:
+        like = next(t for t in tens if t is not None)
+        flat = torch.zeros(total, dtype=torch.float32, device=like.device)
+        for i, o in offs.items():
+            bufs[i] = rets[i] = flat[o:o + tens[i].numel()].view(tens[i].shape)
+    return bufs, rets
 
 
 def _fill_wa(p: _lib.WindowAttnParams, q, kv, residual, out, tensors, cfg) -> None:
@@ -437,6 +462,8 @@ class _WindowAttn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.self_attn = kv is None
         ctx.has_residual = residual is not None
+        # x + Attn(LN(x)): the residual is the query source itself -> its gradient (= gout) is added inside the backward
+        ctx.fold_residual = residual is not None and residual.data_ptr() == q.data_ptr() and residual.shape == q.shape
         ctx.save_for_backward(q, kv_t, *tensors)
         return out
 
@@ -451,14 +478,15 @@ class _WindowAttn(torch.autograd.Function):
         _fill_wa(p.fwd, q, kv_t, None, dummy_out, tens, ctx.cfg)
         gq = torch.empty_like(q)
         gkv = None if ctx.self_attn else torch.empty_like(kv_t)
-        grads = _zero_grads_like(tens)
+        bufs, grads = _param_grad_buffers(tensors, tens)
         p.gout, p.g_q_src, p.g_kv_src = gout.data_ptr(), gq.data_ptr(), _ptr(gkv)
-        for name, g in zip(_WA_TENSORS, grads):
+        for name, g in zip(_WA_TENSORS, bufs):
             setattr(p, "g_" + name, _ptr(g))
+        p.add_to_g_q_src = gout.data_ptr() if ctx.fold_residual else None
         nbytes = lib.sf_window_attn_bwd_workspace_bytes(C.byref(p))
         ws, wsp = _workspace(nbytes, q)
         check(lib.sf_window_attn_bwd(C.byref(p), wsp, nbytes, _stream()), "sf_window_attn_bwd")
-        gres = gout if ctx.has_residual else None
+        gres = gout if (ctx.has_residual and not ctx.fold_residual) else None
         return (gq, gkv, gres, *grads, None)
 
 
@@ -517,7 +545,8 @@ class _Mlp(torch.autograd.Function):
         nbytes = lib.sf_mlp_workspace_bytes(C.byref(p))
         ws, wsp = _workspace(nbytes, x)
         check(lib.sf_mlp_fwd(C.byref(p), wsp, nbytes, _stream()), "sf_mlp_fwd")
-        ctx.cfg = (eps, prec, residual is not None)
+        fold = residual is not None and residual.data_ptr() == x.data_ptr() and residual.shape == x.shape
+        ctx.cfg = (eps, prec, residual is not None, fold)
         ctx.save_for_backward(x, ln_g, ln_b, w1, b1, w2, b2)
         return out
 
@@ -526,19 +555,20 @@ class _Mlp(torch.autograd.Function):
         lib = _lib.load()
         gout = _g(gout)
         x, *tensors = ctx.saved_tensors
-        eps, prec, has_res = ctx.cfg
+        eps, prec, has_res, fold = ctx.cfg
         tens = [_param(t, n) for n, t in zip(_MLP_TENSORS, tensors)]
         p = _lib.MlpBwdParams()
         _fill_mlp(p.fwd, x, None, gout, tens, eps, prec)
         gin = torch.empty_like(x)
-        grads = _zero_grads_like(tens)
+        bufs, grads = _param_grad_buffers(tensors, tens)
         p.gout, p.g_in = gout.data_ptr(), gin.data_ptr()
-        for name, g in zip(_MLP_TENSORS, grads):
+        for name, g in zip(_MLP_TENSORS, bufs):
             setattr(p, "g_" + name, _ptr(g))
+        p.add_to_g_in = gout.data_ptr() if fold else None
         nbytes = lib.sf_mlp_bwd_workspace_bytes(C.byref(p))
         ws, wsp = _workspace(nbytes, x)
         check(lib.sf_mlp_bwd(C.byref(p), wsp, nbytes, _stream()), "sf_mlp_bwd")
-        return (gin, gout if has_res else None, *grads, None, None)
+        return (gin, gout if (has_res and not fold) else None, *grads, None, None)
 
 
 def mlp(x: Tensor, *, w1, b1, w2, b2, ln=None, residual: Optional[Tensor] = None, eps: float = 1e-5,

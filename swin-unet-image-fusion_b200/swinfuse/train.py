@@ -103,6 +103,8 @@ class DataParallelTrainer:
                  use_graph: bool = False):
         self.model, self.loss_fn, self.group, self.n_buckets = model, loss_fn, group, n_buckets
         self.flat = FlatParameters(model.parameters())
+        from . import ops
+        ops.set_direct_param_grads(True)   # every .grad is a zeroed view of the flat buffer: kernels accumulate into it
         self.opt = FlatAdam(self.flat, lr=lr)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.use_graph = use_graph

@@ -269,3 +269,35 @@ def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted
         floor = 0.05 * gscale if n not in ("gq", "gkv") else 0.0
         e = float((res["bf16"][n] - ref).abs().max()) / max(float(ref.abs().max()), floor)
         assert e <= 1e-2, (n, e)
+
+
+def test_direct_parameter_gradient_accumulation_equals_autograd_accumulation():
+    """ops.set_direct_param_grads(True) (what swinfuse.train.DataParallelTrainer switches on): the kernels add parameter
+    gradients straight into pre-existing .grad buffers instead of returning tensors for autograd to add.  Same numbers
+    (up to the order of the fp32 atomics), and gradients accumulate over two backward passes like autograd's do."""
+    sw = dropin()
+    g = golden("model_small.npz")
+    cfg = small_cfg()
+    ir, vis = fo.synth_inputs(2, 37, 45, seed=5)
+    res = {}
+    for direct in (False, True):
+        m = build_model(cfg, act=nn.ELU()).train()
+        m.load_state_dict(fo.synth_state_dict(cfg, seed=3), strict=True)
+        params = {n: p for n, p in m.named_parameters()}
+        if direct:
+            for p in params.values():
+                p.grad = torch.zeros_like(p)
+        sw.ops.set_direct_param_grads(direct)
+        try:
+            for _ in range(2):
+                out = m(ir.cuda(), vis.cuda())
+                (out * T(g["grad_weight"]).cuda()).sum().backward()
+        finally:
+            sw.ops.set_direct_param_grads(False)
+        res[direct] = {n: p.grad.detach().cpu().clone() for n, p in params.items()}
+    gscale = float(np.median([float(v.abs().max()) for v in res[False].values()]))
+    for n, ref in res[False].items():
+        if n.endswith("k_for_heads.bias") or n == "final_layer.0.bias":
+            continue   # analytically zero gradients: round-off of the atomics' order on both sides
+        e = float((res[True][n] - ref).abs().max()) / max(float(ref.abs().max()), 0.05 * gscale)
+        assert e <= 1e-4, (n, e)
