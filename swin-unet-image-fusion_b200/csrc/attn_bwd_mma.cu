@@ -31,7 +31,8 @@ struct __align__(16) ItemSmem {
     uint32_t q[KC][64 * RSW], k[KC][64 * RSW], v[KC][64 * RSW], g[KC][64 * RSW];
     uint32_t qt[KC][16 * TSW], kt[KC][16 * TSW], gt[KC][16 * TSW], vt[KC][16 * TSW];
     float4 red[WARPS][14][32];      // per-warp partial dK^T / dV^T accumulator fragments
-    long long rows2[2][T + 1];      // double-buffered by item parity: the tail of item i reads them while item i+1 is set up
+    uint32_t rows2[2][64];          // element offset (token row * inner, < 2^32: checked by the launcher) of every token of the
+                                    // window; double-buffered by item parity: the tail of item i reads them while item i+1 is set up
     int reg2[2][64];
     float tab[176], gtab[176];
     float wmax[WARPS];
@@ -69,12 +70,12 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // gather one operand: element e = token * D + dd (flat over the 49 x D block), threads take e = tid + 128 i
 template <int D, int NE>
-__device__ __forceinline__ void load_flat(const float* __restrict__ src, const long long* rows, int inner, int hoff, float (&r)[NE]) {
+__device__ __forceinline__ void load_flat(const float* __restrict__ src, const uint32_t* rows, uint32_t hoff, float (&r)[NE]) {
 #pragma unroll
     for (int i = 0; i < NE; i++) {
         const int e = threadIdx.x + WARPS * 32 * i;
         const int tk = e / D, dd = e - tk * D;
-        r[i] = e < T * D ? __ldg(src + rows[tk] * inner + hoff + dd) : 0.f;
+        r[i] = e < T * D ? __ldg(src + (rows[tk] + hoff + (uint32_t)dd)) : 0.f;
     }
 }
 template <int D, int NE>
@@ -140,20 +141,20 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(co
         const int win = (int)(blockIdx.x / nh), head = (int)(blockIdx.x - (long long)win * nh);
         if (threadIdx.x < T) {
             int rg;
-            ws->rows2[0][threadIdx.x] = win_token_src(g, win, threadIdx.x, &rg);
+            ws->rows2[0][threadIdx.x] = (uint32_t)(win_token_src(g, win, threadIdx.x, &rg) * inner);
             ws->reg2[0][threadIdx.x] = rg;
         }
         __syncthreads();
-        load_flat<D, NE>(gO, ws->rows2[0], inner, head * D, pd);
-        load_flat<D, NE>(Q, ws->rows2[0], inner, head * D, pa);
-        load_flat<D, NE>(K, ws->rows2[0], inner, head * D, pb);
-        load_flat<D, NE>(V, ws->rows2[0], inner, head * D, pc);
+        load_flat<D, NE>(gO, ws->rows2[0], (uint32_t)(head * D), pd);
+        load_flat<D, NE>(Q, ws->rows2[0], (uint32_t)(head * D), pa);
+        load_flat<D, NE>(K, ws->rows2[0], (uint32_t)(head * D), pb);
+        load_flat<D, NE>(V, ws->rows2[0], (uint32_t)(head * D), pc);
     }
     int parity = 0;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
         const int win = (int)(item / nh), head = (int)(item - (long long)win * nh);
         const int hoff = head * D;
-        const long long* rows = ws->rows2[parity];
+        const uint32_t* rows = ws->rows2[parity];
         const int* reg = ws->reg2[parity];
         const long long nitem = item + gridDim.x;
         const int nwin = (int)(nitem / nh), nhead = (int)(nitem - (long long)nwin * nh);
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(co
             store_flat<D, NE>(pc, reinterpret_cast<__half*>(ws->v[0]), reinterpret_cast<__half*>(ws->vt[0]), 1.f);
             if (nitem < nitems && threadIdx.x < T) {     // token rows of the next item (other parity: the previous item's tail is over)
                 int rg;
-                ws->rows2[parity ^ 1][threadIdx.x] = win_token_src(g, nwin, threadIdx.x, &rg);
+                ws->rows2[parity ^ 1][threadIdx.x] = (uint32_t)(win_token_src(g, nwin, threadIdx.x, &rg) * inner);
                 ws->reg2[parity ^ 1][threadIdx.x] = rg;
             }
             __syncthreads();
@@ -181,10 +182,10 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(co
             inv_sc = __int_as_float(ex << 23);                        // (mx == 0: every output is 0 * 0)
             store_flat<D, NE>(pd, reinterpret_cast<__half*>(ws->g[0]), reinterpret_cast<__half*>(ws->gt[0]), sc);
             if (nitem < nitems) {
-                load_flat<D, NE>(gO, ws->rows2[parity ^ 1], inner, nhead * D, pd);
-                load_flat<D, NE>(Q, ws->rows2[parity ^ 1], inner, nhead * D, pa);
-                load_flat<D, NE>(K, ws->rows2[parity ^ 1], inner, nhead * D, pb);
-                load_flat<D, NE>(V, ws->rows2[parity ^ 1], inner, nhead * D, pc);
+                load_flat<D, NE>(gO, ws->rows2[parity ^ 1], (uint32_t)(nhead * D), pd);
+                load_flat<D, NE>(Q, ws->rows2[parity ^ 1], (uint32_t)(nhead * D), pa);
+                load_flat<D, NE>(K, ws->rows2[parity ^ 1], (uint32_t)(nhead * D), pb);
+                load_flat<D, NE>(V, ws->rows2[parity ^ 1], (uint32_t)(nhead * D), pc);
             }
         }
         __syncthreads();
@@ -312,12 +313,12 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(co
                     const int dd = 16 * kc + 8 * nd + 2 * tq + e;
                     if (nd < ndt && dd < D) {
                         if (r0 < T) {
-                            const long long o0 = rows[r0] * inner + hoff + dd;
+                            const uint32_t o0 = rows[r0] + (uint32_t)(hoff + dd);
                             dQ[o0] = dq[nd][e] * f;
                             if (O) O[o0] = o[nd][e];
                         }
                         if (r1 < T) {
-                            const long long o1 = rows[r1] * inner + hoff + dd;
+                            const uint32_t o1 = rows[r1] + (uint32_t)(hoff + dd);
                             dQ[o1] = dq[nd][2 + e] * f;
                             if (O) O[o1] = o[nd][2 + e];
                         }
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(co
                 for (int e = 0; e < 2; e++) {
                     const int key = 8 * n + 2 * tq + e;
                     if (key < T) {
-                        const long long o = rows[key] * inner + hoff;
+                        const uint32_t o = rows[key] + (uint32_t)hoff;
                         if (d0 < D) dst[o + d0] = acc[e] * f;
                         if (d0 + 8 < D) dst[o + d0 + 8] = acc[2 + e] * f;
                     }
@@ -403,7 +404,11 @@ int launch_one(const float* Q, const float* K, const float* V, const float* gO, 
 
 }  // namespace
 
-bool attn_core_bwd_mma_supported(const WinGeom& g, int d) { return g.wsh == 7 && g.wsw == 7 && (d == 3 || d == 6 || d == 12 || d == 24 || d == 48); }
+bool attn_core_bwd_mma_supported(const WinGeom& g, int d, int nh) {
+    // element offsets inside the kernel are 32-bit
+    return g.wsh == 7 && g.wsw == 7 && (d == 3 || d == 6 || d == 12 || d == 24 || d == 48) &&
+           (long long)g.B * g.Hp * g.Wp * nh * d < (1LL << 32);
+}
 
 int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
                              const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st) {

@@ -12,7 +12,7 @@ int patch_bwd(const sf_patch_bwd_params* p, void* ws, size_t ws_bytes, cudaStrea
 size_t head_bwd_ws(const sf_head_bwd_params* p);
 int head_bwd(const sf_head_bwd_params* p, void* ws, size_t ws_bytes, cudaStream_t st);
 // attn_bwd_mma.cu: tensor-core attention-core backward (7x7 windows, head_dim 3 / 6 / 12)
-bool attn_core_bwd_mma_supported(const WinGeom& g, int d);
+bool attn_core_bwd_mma_supported(const WinGeom& g, int d, int nh);
 // O (optional): also writes the forward output P V, so that the caller need not recompute the attention core
 int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
                              const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st);

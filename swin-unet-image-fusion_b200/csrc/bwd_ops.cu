@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(64) k_attn_core_bwd_w7(const float* __restrict
 static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
                                 const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st,
                                 bool tensor_cores, float* O_out = nullptr) {
-    if (tensor_cores && attn_core_bwd_mma_supported(g, d))
+    if (tensor_cores && attn_core_bwd_mma_supported(g, d, nh))
         return launch_attn_core_bwd_mma(Q, K, V, gO, dQ, dK, dV, O_out, table, gtable, g, inner, nh, d, st);
     const int tabn = (2 * g.wsh - 1) * (2 * g.wsw - 1);
     size_t smem = ((size_t)4 * g.T * d + 2 * (size_t)g.T * (g.T + 1) + 2 * tabn + 2) * sizeof(float) + (size_t)g.T * 12 + 16;
@@ -717,7 +717,7 @@ int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws
     SF_TRY(tf ? gemm_tf32_nt(gb, 3, M, inner, C, st) : launch_gemm_tn(gb, 3, M, inner, C, false, st));
     WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
     // the tensor-core adjoint of the attention core also delivers O = P V (one more product on fragments it already holds)
-    const bool fused_o = tf && attn_core_bwd_mma_supported(geom, p->head_dim);
+    const bool fused_o = tf && attn_core_bwd_mma_supported(geom, p->head_dim, p->num_heads);
     if (!fused_o) SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
     // ---- output projection: gradient w.r.t. O -----------------------------------------------------------
     SF_TRY(launch_gemm_nn(bp->gout, p->wo, nullptr, gO, M, inner, C, false, st, tf));
