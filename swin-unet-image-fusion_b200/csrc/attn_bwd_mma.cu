@@ -96,7 +96,7 @@ __device__ __forceinline__ void store_flat(const float (&r)[NE], __half* rowmajo
 // One CTA (4 warps) per (window, head); warp m owns query rows 16 m .. 16 m + 15, so every lane meets the same 28
 // (query, key) positions on every item and the bias-table gradient is accumulated in 28 registers.
 template <int D>
-__global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 4 : 2) k_attn_bwd_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+__global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                                                              const float* __restrict__ gO, float* __restrict__ dQ, float* __restrict__ dK,
                                                              float* __restrict__ dV, float* __restrict__ O, const float* __restrict__ table,
                                                              float* __restrict__ gtable, WinGeom g, int inner, int nh, float scale, long long nitems) {
@@ -395,7 +395,7 @@ int launch_one(const float* Q, const float* K, const float* V, const float* gO, 
         if (e != cudaSuccess) { set_error("attention backward (mma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
         configured = true;
     }
-    long long grid = 148LL * (D <= 16 ? 4 : 2);
+    long long grid = 148LL * (D <= 16 ? 3 : 2);
     if (grid > nitems) grid = nitems;
     k_attn_bwd_mma<D><<<(unsigned)grid, WARPS * 32, smem, st>>>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, 1.0f / sqrtf((float)D), nitems);
     SF_CHECK_LAUNCH("bwd_attn_core_mma");
