@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
     constexpr int KC = (D + 15) / 16;     // 16-wide chunks of the head dimension
     extern __shared__ __align__(16) unsigned char smraw[];
     ItemSmem<KC>* ws = reinterpret_cast<ItemSmem<KC>*>(smraw);
+    float2* red2 = reinterpret_cast<float2*>(&ws->red[0][0][0]);   // narrow heads (D <= 8) exchange float2 partials: [warp * 14 + fragment][lane]
     const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
         uint32_t* ops = reinterpret_cast<uint32_t*>(ws);                 // q, k, v, g, qt, kt, gt, vt are contiguous
@@ -340,16 +341,32 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
                     float pk[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
                     mma16816(pk, qa0, qa1, qa2, qa3, movm_trans(dsh[n][0]), movm_trans(dsh[n][1]));
                     mma16816(pv, ga0, ga1, ga2, ga3, movm_trans(ph[n][0]), movm_trans(ph[n][1]));
-                    ws->red[m][n][lane] = make_float4(pk[0], pk[1], pk[2], pk[3]);
-                    ws->red[m][7 + n][lane] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                    if constexpr (D <= 8) {     // fragment rows gq + 8 (dims 8..15) do not exist and only lanes gq < D hold real dims:
+                        if (gq < D) {           // 8-byte stores from a quarter of the lanes = a quarter of the shared-memory wavefronts
+                            red2[(m * 14 + n) * 32 + lane] = make_float2(pk[0], pk[1]);
+                            red2[(m * 14 + 7 + n) * 32 + lane] = make_float2(pv[0], pv[1]);
+                        }
+                    } else {
+                        ws->red[m][n][lane] = make_float4(pk[0], pk[1], pk[2], pk[3]);
+                        ws->red[m][7 + n][lane] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                    }
                 }
             }
             __syncthreads();
             // warp m finishes fragments m, m+4, m+8, m+12: (row = dim gq / gq+8 of the chunk, col = key 8 n + 2 tq + e)
 #pragma unroll
             for (int i = m; i < 14; i += WARPS) {
-                const float4 p0 = ws->red[0][i][lane], p1 = ws->red[1][i][lane], p2 = ws->red[2][i][lane], p3 = ws->red[3][i][lane];
-                const float acc[4] = {(p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w)};
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if constexpr (D <= 8) {
+                    if (gq < D) {
+                        const float2 p0 = red2[i * 32 + lane], p1 = red2[(14 + i) * 32 + lane], p2 = red2[(28 + i) * 32 + lane], p3 = red2[(42 + i) * 32 + lane];
+                        acc[0] = (p0.x + p1.x) + (p2.x + p3.x); acc[1] = (p0.y + p1.y) + (p2.y + p3.y);
+                    }
+                } else {
+                    const float4 p0 = ws->red[0][i][lane], p1 = ws->red[1][i][lane], p2 = ws->red[2][i][lane], p3 = ws->red[3][i][lane];
+                    acc[0] = (p0.x + p1.x) + (p2.x + p3.x); acc[1] = (p0.y + p1.y) + (p2.y + p3.y);
+                    acc[2] = (p0.z + p1.z) + (p2.z + p3.z); acc[3] = (p0.w + p1.w) + (p2.w + p3.w);
+                }
                 const bool isk = i < 7;
                 const int n = isk ? i : i - 7;
                 float* dst = isk ? dK : dV;
