@@ -2,9 +2,11 @@
 // reference defines no custom backward (pure autograd, a016:164); these kernels restate the
 // adjoints of a001/a003/a004/a011/a013 and are checked against autograd over the oracle.
 //
-// Every backward recomputes the forward intermediates from the operator inputs in fp32 (nothing
-// but the inputs is saved by the forward pass).  Weight / bias / table gradients are ACCUMULATED
-// into caller-zeroed buffers with fp32 atomics; activation gradients are written.
+// Every backward recomputes the forward intermediates from the operator inputs (nothing but the
+// inputs is saved by the forward pass): exact fp32 FFMA kernels for SF_PREC_FP32 operators, TF32 /
+// fp16 tensor-core kernels with fp32 accumulation for SF_PREC_BF16 operators (gemm_tf32.cu,
+// attn_bwd_mma.cu).  Weight / bias / table gradients are ACCUMULATED into caller-zeroed buffers
+// with fp32 atomics; activation gradients are written.
 #include "bwd_kernels.cuh"
 #include "fp32_kernels.cuh"
 
