@@ -137,9 +137,51 @@ def cpu_forward_pairs_per_s(n_pairs: int, size: int, reps: int, warmup: int):
     return dict(best_s=best, mean_s=mean, threads=torch.get_num_threads(), pairs=n_pairs)
 
 
+def cpu_train_pairs_per_s(n_pairs: int, size: int, reps: int, warmup: int):
+    """One training step of the reference path on the host cores: oracle forward (train mode: batch-stat BatchNorm,
+    a013:133) -> clamp (a016:153) -> a008 loss (dense restatement of the kornia formulation) -> autograd backward.
+    No optimizer step (a few ms on the CPU).  SURVEY 8(d): B=4, nn.ELU() semantics."""
+    from oracle import fusion_oracle as fo
+    from oracle import kornia_restatement as kr
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "num_batches" not in k else v.clone())
+          for k, v in fo.synth_state_dict().items()}
+    ir, vis = fo.synth_inputs(n_pairs, size, size)
+    ms, sobel = kr.MS_SSIMLoss(), kr.Sobel()
+    leaves = [v for v in sd.values() if v.requires_grad]
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        fusion = torch.clamp(fo.model_forward(sd, ir, vis, training=True), 0, 1)
+        loss = kr.total_loss(fusion, ir, vis, ms, sobel)
+        torch.autograd.grad(loss, leaves, allow_unused=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return dict(best_s=min(times), mean_s=sum(times) / len(times), threads=torch.get_num_threads(), pairs=n_pairs)
+
+
+def run_reference_train(args):
+    n = max(1, min(args.cpu_sample if args.cpu_sample > 0 else 4, args.batch))
+    r = cpu_train_pairs_per_s(n, args.size, reps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    value = n / r["mean_s"]
+    sample = (f"{n} of {args.batch} pairs per step ({args.size}x{args.size}, fp32 oracle forward + dense a008 loss restatement + "
+              f"autograd backward, torch CPU ops)")
+    line = {"impl": "reference", "metric": "training image pairs/sec", "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": max(1, min(args.steps, 3)), "warmup": min(args.warmup, 1), "ms_per_step": r["mean_s"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"training step B={args.batch}/GPU {args.size}x{args.size} pairs (BASELINE configs[2])", "step": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    emit(line)
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
+    if args.mode == "train":
+        return run_reference_train(args)
     n = max(1, min(args.cpu_sample if args.cpu_sample > 0 else 4, args.batch))
     r = cpu_forward_pairs_per_s(n, args.size, reps=max(1, args.steps), warmup=min(args.warmup, 1))
     value = n / r["mean_s"]
@@ -406,6 +448,13 @@ def run_train(args, rank: int, world: int, local_rank: int):
     if rank != 0:
         return
     pairs = B * world * args.steps
+    cpu = None
+    if world == 1 and args.cpu_sample > 0:   # the reference path's training step on this box's host cores, bounded sample
+        n = max(1, min(args.cpu_sample, B))
+        r = cpu_train_pairs_per_s(n, S, reps=1, warmup=1)
+        cpu = {"value": n / r["mean_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": f"{n} of {B} pairs, {S}x{S}: fp32 oracle forward (train mode) + dense a008 loss restatement + autograd backward, "
+                         f"torch CPU ops, 1 step after 1 warm-up"}
     kernels = {k: {"launches_per_step": v["launches"], "ms_per_step": v["total_ms"]} for k, v in
                sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}
     line = {"metric": "training image pairs/sec", "value": pairs / (ms / 1e3), "unit": UNIT, "n_gpus": world,
@@ -418,7 +467,8 @@ def run_train(args, rank: int, world: int, local_rank: int):
                        "collective": "one NCCL all-reduce of the flat fp32 gradient buffer" if world > 1 else "none",
                        "launch": "eager" if args.no_graph else "cuda-graph replay of zero-grad + forward + loss + backward; all-reduce + Adam eager"},
             "gpu_launches": launches * args.steps, "loss_first": float(loss0), "loss_last": float(loss), "clocks": clocks,
-            "model_tflops": pairs / (ms / 1e3) * 3 * GFLOP_PER_PAIR_256 * (S / 256.0) ** 2 / 1e3, "kernels": kernels}
+            "model_tflops": pairs / (ms / 1e3) * 3 * GFLOP_PER_PAIR_256 * (S / 256.0) ** 2 / 1e3, "kernels": kernels,
+            "cpu_baseline": cpu}
     emit(line)
 
 
