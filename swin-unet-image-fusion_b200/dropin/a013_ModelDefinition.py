@@ -53,7 +53,7 @@ class MyModel(nn.Module):
 
     def do_final_layer(self, x, y):
         conv1, bn, _, conv2 = self.final_layer
-        use_batch_stats = self.training or bn.running_mean is None
+        use_batch_stats = bn.training or bn.running_mean is None   # nn.BatchNorm2d decides by its OWN mode flag
         if bn.momentum is None or not bn.track_running_stats or not bn.affine:
             raise ops.SwinFuseError("MyModel: the head expects the default nn.BatchNorm2d(2) (a013:133)")
         out = ops.final_head(x, y, w1=conv1.weight, b1=conv1.bias, bn_gamma=bn.weight, bn_beta=bn.bias,

@@ -163,24 +163,43 @@ def invalidate_packed_cache() -> None:
     _weights_epoch += 1
 
 
-def _packed_weights(holder, key_tensors, nbytes_fn, pack_fn, p, like: Tensor, what: str):
+def _packed_weights(holder, key_tensors, nbytes_fn, pack_fn, p, like: Tensor, what: str, variant=()):
     """bf16 tensor-core operand images of the weights: packed once per weight version, owned by the
-    caller side (stored on the parameter object), passed to the library through ``params.packed``."""
+    caller side (stored on the parameter object), passed to the library through ``params.packed``.
+
+    The image of a (holder, variant) pair lives in ONE buffer for the life of the holder: a stale image is
+    re-packed in place, never re-allocated, so a CUDA graph that recorded the buffer's address stays valid
+    whatever runs eagerly between replays.  ``variant`` carries everything besides the weight values that
+    decides the image's layout (self / cross plan, geometry class, byte size): a module called both ways
+    keeps one image per layout.  During stream capture a stale image is re-packed by kernels recorded INTO
+    the graph, so every replay packs the weights of that moment (training: sf_adam_step rewrites them
+    between replays)."""
     if p.precision != SF_PREC_BF16 or holder is None:
         return None
-    key = (_weights_epoch, tuple((t.data_ptr(), t._version) for t in key_tensors if t is not None))
-    cached = getattr(holder, "_sf_packed", None)
-    if cached is not None and cached[0] == key:
-        return cached[1]
     nbytes = nbytes_fn(C.byref(p))
     if nbytes == 0:
         return None
-    buf = torch.empty(nbytes, dtype=torch.uint8, device=like.device)
+    variant = (tuple(variant), int(nbytes), like.device.index)
+    key = (_weights_epoch, tuple((t.data_ptr(), t._version) for t in key_tensors if t is not None))
+    store = getattr(holder, "_sf_packed", None)
+    if not isinstance(store, dict):
+        store = {}
+        try:
+            holder._sf_packed = store
+        except AttributeError:
+            pass
+    cached = store.get(variant)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    if cached is not None:
+        buf = cached[1]
+    else:
+        if torch.cuda.is_current_stream_capturing():
+            raise SwinFuseError(f"{what}: the packed-weight buffer must exist before stream capture "
+                                f"(run one eager warm-up call of the module first)")
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=like.device)
     check(pack_fn(C.byref(p), buf.data_ptr(), nbytes, _stream()), what)
-    try:
-        holder._sf_packed = (key, buf)
-    except AttributeError:
-        pass
+    store[variant] = (key, buf)
     return buf
 
 
@@ -453,8 +472,10 @@ class _WindowAttn(torch.autograd.Function):
         tens = [_param(t, n) for n, t in zip(_WA_TENSORS, tensors)]
         p = _lib.WindowAttnParams()
         _fill_wa(p, q, kv_t, residual, out, tens, cfg)
+        # the image layout depends on self / cross and on the frag plan (7x7 windows below the index-range limit)
+        variant = (kv is None, b * h * w >= (2 ** 31 - 1) // 64, cfg[2], cfg[3], cfg[0], cfg[1])
         packed = _packed_weights(tensors[4], tens[4:12], lib.sf_window_attn_packed_bytes, lib.sf_window_attn_pack, p, q,
-                                 "sf_window_attn_pack")
+                                 "sf_window_attn_pack", variant)
         p.packed = _ptr(packed)
         nbytes = lib.sf_window_attn_workspace_bytes(C.byref(p))
         ws, wsp = _workspace(nbytes, q)

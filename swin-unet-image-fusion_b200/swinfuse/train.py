@@ -7,6 +7,7 @@ the optimizer is one sf_adam_step kernel over the flat buffers (torch.optim.Adam
 """
 from __future__ import annotations
 
+import math
 from typing import Iterable, List, Optional
 
 import torch
@@ -68,6 +69,51 @@ class FlatParameters:
             w.wait()
 
 
+class CosineWarmRestarts:
+    """Host-side learning-rate schedule of a016:68-72 / a016:109-113: torch's CosineAnnealingWarmRestarts(T_0, T_mult=1,
+    eta_min) stepped with a fractional epoch ``epoch - 1 + (iter - 1) / iters_per_epoch``:
+
+        lr(t) = eta_min + (base_lr - eta_min) * (1 + cos(pi * (t mod T_0) / T_0)) / 2
+
+    A plain closed form evaluated on the host: the only consumer is the ``lr`` scalar argument of sf_adam_step."""
+
+    def __init__(self, base_lr: float, T_0: int, eta_min: float = 0.0, T_mult: int = 1):
+        if T_0 <= 0 or not isinstance(T_0, int):
+            raise ValueError(f"Expected positive integer T_0, but got {T_0}")
+        if T_mult < 1 or not isinstance(T_mult, int):
+            raise ValueError(f"Expected integer T_mult >= 1, but got {T_mult}")
+        self.base_lr, self.T_0, self.eta_min, self.T_mult = float(base_lr), T_0, float(eta_min), T_mult
+        self.last_epoch = 0.0
+        self.last_lr = self.base_lr
+
+    def lr_at(self, epoch: float) -> float:
+        if epoch < 0:
+            raise ValueError(f"Expected non-negative epoch, but got {epoch}")
+        if epoch >= self.T_0:
+            if self.T_mult == 1:
+                t_cur, t_i = epoch % self.T_0, self.T_0
+            else:
+                n = int(math.log(epoch / self.T_0 * (self.T_mult - 1) + 1, self.T_mult))
+                t_cur = epoch - self.T_0 * (self.T_mult ** n - 1) / (self.T_mult - 1)
+                t_i = self.T_0 * self.T_mult ** n
+        else:
+            t_cur, t_i = epoch, self.T_0
+        return self.eta_min + (self.base_lr - self.eta_min) * (1 + math.cos(math.pi * t_cur / t_i)) / 2
+
+    def step(self, epoch: float) -> float:
+        self.last_epoch = float(epoch)
+        self.last_lr = self.lr_at(epoch)
+        return self.last_lr
+
+    def state_dict(self) -> dict:
+        return dict(base_lr=self.base_lr, T_0=self.T_0, eta_min=self.eta_min, T_mult=self.T_mult,
+                    last_epoch=self.last_epoch, last_lr=self.last_lr)
+
+    def load_state_dict(self, sd: dict) -> None:
+        for k in ("base_lr", "T_0", "eta_min", "T_mult", "last_epoch", "last_lr"):
+            setattr(self, k, sd[k])
+
+
 class FlatAdam:
     """Adam over FlatParameters with the library's sf_adam_step kernel (CUDA) -- one launch per step."""
 
@@ -76,6 +122,44 @@ class FlatAdam:
         self.exp_avg = torch.zeros_like(flat.flat_param)
         self.exp_avg_sq = torch.zeros_like(flat.flat_param)
         self.step_count = 0
+
+    def state_dict(self) -> dict:
+        """The layout ``torch.optim.Adam(model.parameters()).state_dict()`` has (a016:238-250 saves that): per-parameter
+        ``step`` / ``exp_avg`` / ``exp_avg_sq`` in parameter order, one param group."""
+        f = self.flat
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(f.params, f.offsets)):
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[o:o + p.numel()].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(f.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        """Accepts a torch.optim.Adam state dict over the same parameter list (a016:306-339)."""
+        f = self.flat
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(f.params):
+            raise ValueError(f"optimizer state has {len(group['params'])} parameters, the model has {len(f.params)}")
+        if group.get("weight_decay", 0) or group.get("amsgrad", False) or group.get("maximize", False):
+            raise ValueError("FlatAdam implements plain Adam only (a016:67): no weight decay / amsgrad / maximize")
+        self.lr, self.betas, self.eps = float(group["lr"]), tuple(group["betas"]), float(group["eps"])
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, (p, o) in enumerate(zip(f.params, f.offsets)):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            steps.add(int(float(st["step"])))
+            self.exp_avg[o:o + p.numel()].view_as(p).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+        if len(steps) > 1:
+            raise ValueError(f"FlatAdam keeps one step count for all parameters, the state has {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
 
     def step(self, grad_scale: float = 1.0) -> None:
         from . import _lib
@@ -100,13 +184,22 @@ class DataParallelTrainer:
     Shapes must then stay fixed; a new shape re-captures."""
 
     def __init__(self, model: torch.nn.Module, loss_fn, lr: float = 1e-2, group=None, n_buckets: int = 1,
-                 use_graph: bool = False):
+                 use_graph: bool = False, scheduler: Optional[CosineWarmRestarts] = None, sync_init: bool = True):
         self.model, self.loss_fn, self.group, self.n_buckets = model, loss_fn, group, n_buckets
         self.flat = FlatParameters(model.parameters())
-        from . import ops
-        ops.set_direct_param_grads(True)   # every .grad is a zeroed view of the flat buffer: kernels accumulate into it
-        self.opt = FlatAdam(self.flat, lr=lr)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if sync_init and self.world > 1:
+            # replicas must start identical (a016:42 initialises with kaiming-normal draws from the per-process RNG):
+            # rank 0's parameters and buffers (BatchNorm running statistics of the head, a013:133) win, as in DDP
+            dist.broadcast(self.flat.flat_param, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            for b in model.buffers():
+                dist.broadcast(b, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        from . import ops
+        if self.flat.flat_param.is_cuda:
+            ops.set_direct_param_grads(True)   # every .grad is a zeroed view of the flat buffer: kernels accumulate into it
+            ops.invalidate_packed_cache()      # the parameters moved into the flat buffer (and may have been broadcast over)
+        self.opt = FlatAdam(self.flat, lr=lr)
+        self.scheduler = scheduler
         self.use_graph = use_graph
         self._graph, self._shape, self._eager_steps = None, None, 0
 
@@ -126,6 +219,11 @@ class DataParallelTrainer:
         with torch.cuda.stream(side):   # autograd's stream bookkeeping wants a warm-up on the capturing side stream
             self._forward_backward(self._ir, self._vis)
         torch.cuda.current_stream().wait_stream(side)
+        # Every bf16 operand image is stale from here on, so the capture below RECORDS the pack kernels (into the
+        # buffers the warm-up allocated): each replay then packs the weights sf_adam_step left behind.  Without this
+        # the captured forward would find fresh images, record no pack kernel and replay on frozen weights.
+        from . import ops
+        ops.invalidate_packed_cache()
         self._graph = torch.cuda.CUDAGraph()
         # the autograd engine runs backward nodes (and their allocations) on its own thread: thread-local capture mode
         with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
@@ -149,3 +247,27 @@ class DataParallelTrainer:
         self.flat.all_reduce_grads(self.group, self.n_buckets)
         self.opt.step(grad_scale=1.0 / self.world)
         return loss
+
+    def set_epoch(self, epoch: float) -> float:
+        """a016:109-113 (``use_scheduler``): called after the optimizer step with the fractional epoch; the new learning
+        rate is what the next sf_adam_step receives."""
+        if self.scheduler is None:
+            return self.opt.lr
+        self.opt.lr = self.scheduler.step(epoch)
+        return self.opt.lr
+
+    def state_dict(self, current_epoch: int = 0) -> dict:
+        """The checkpoint a016:238-250 writes: model / optimizer / scheduler state and the finished epoch."""
+        return {"model_state": self.model.state_dict(), "optimizer_state": self.opt.state_dict(),
+                "scheduler_state": None if self.scheduler is None else self.scheduler.state_dict(),
+                "current_epoch": current_epoch}
+
+    def load_state_dict(self, state: dict) -> int:
+        """a016:306-339.  Parameters are written into the flat buffer in place (the views stay attached)."""
+        self.model.load_state_dict(state["model_state"])
+        self.opt.load_state_dict(state["optimizer_state"])
+        if self.scheduler is not None and state.get("scheduler_state") is not None:
+            self.scheduler.load_state_dict(state["scheduler_state"])
+        from . import ops
+        ops.invalidate_packed_cache()
+        return int(state.get("current_epoch", 0)) + 1
