@@ -20,6 +20,18 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& c = cached[dev & 63];
+    if (c == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        c = v;
+    }
+    return c;
+}
 void count_launch(int n) { g_launches += n; }
 
 const char* prof_name(const char* fmt, int v) {

@@ -406,13 +406,13 @@ template <int D>
 int launch_one(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O, const float* table,
                float* gtable, const WinGeom& g, int inner, int nh, long long nitems, cudaStream_t st) {
     const size_t smem = sizeof(ItemSmem<(D + 15) / 16>);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_attn_bwd_mma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("attention backward (mma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
-        configured = true;
+        configured.done();
     }
-    long long grid = 148LL * (D <= 16 ? 3 : 2);
+    long long grid = (long long)sm_count() * (D <= 16 ? 3 : 2);
     if (grid > nitems) grid = nitems;
     k_attn_bwd_mma<D><<<(unsigned)grid, WARPS * 32, smem, st>>>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, 1.0f / sqrtf((float)D), nitems);
     SF_CHECK_LAUNCH("bwd_attn_core_mma");

@@ -246,11 +246,11 @@ static int launch_attn_small(const AttnArgs& a, cudaStream_t st) {
     const int inner = a.nh * a.d;
     size_t smem = attn_carve<true>(nullptr, nullptr, TT, a.nh, DP, inner, DP <= 16);
     SF_CHECK_ARG(smem <= 227 * 1024, "attention core: %d heads x %d dims need %zu B of shared memory", a.nh, a.d, smem);
-    static thread_local bool configured = false;
-    if (smem > 48 * 1024 && !configured) {
+    static DeviceOnce configured;
+    if (smem > 48 * 1024 && configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_attn_small<DP, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("attention core: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
-        configured = true;
+        configured.done();
     }
     int threads = (a.nh * TT + 31) / 32 * 32;
     const int maxthr = DP <= 16 ? 416 : 256;
@@ -259,7 +259,7 @@ static int launch_attn_small(const AttnArgs& a, cudaStream_t st) {
     int per_sm = (int)(227 * 1024 / (smem + 1024));
     if (per_sm > (DP <= 8 ? 2 : 1)) per_sm = (DP <= 8 ? 2 : 1);
     if (per_sm < 1) per_sm = 1;
-    long long grid = 148LL * per_sm;
+    long long grid = (long long)sm_count() * per_sm;
     if (grid > a.nwin) grid = a.nwin;
     const double mtok = (double)a.nwin * TT;
     ProfScope ps(prof_name("attn_core_small_c%d", inner), 4.0 * TT * mtok * inner, 8.0 * mtok * inner, st);
@@ -451,11 +451,11 @@ static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
     const int inner = a.nh * a.d;
     size_t smem = attn_carve<SMALL>(nullptr, nullptr, a.g.T, a.nh, a.dp, inner);
     SF_CHECK_ARG(smem <= 227 * 1024, "attention core: window of %d tokens x %d channels needs %zu B of shared memory", a.g.T, inner, smem);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static DeviceOnce configured;
+    if (smem > 48 * 1024 && configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_attn_core<DMAX, TT, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("attention core: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
-        configured = 227 * 1024;
+        configured.done();
     }
     const int items = a.nh * a.g.T;
     const int maxthr = SMALL ? 448 : 256;
@@ -466,7 +466,7 @@ static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
     if (per_sm > 2048 / threads) per_sm = 2048 / threads;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
-    long long grid = 148LL * per_sm;
+    long long grid = (long long)sm_count() * per_sm;
     if (grid > a.nwin) grid = a.nwin;
     const double mtok = (double)a.nwin * a.g.T;
     ProfScope ps(prof_name("attn_core_generic_c%d", inner), 4.0 * a.g.T * mtok * inner, 8.0 * mtok * inner, st);

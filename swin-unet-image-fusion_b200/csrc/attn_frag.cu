@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_attn_pack4(AttnFragArgs a) {
 template <int KSTEPS, int NDT, bool DP4, bool PREFETCH>
 static int launch_attn_frag_t(const AttnFragArgs& a, cudaStream_t st) {
     constexpr int dp = DP4 ? 4 : 8 * NDT;
-    long long grid = 148LL * (PREFETCH ? 2 : 1);
+    long long grid = (long long)sm_count() * (PREFETCH ? 2 : 1);
     if (grid > a.nwin) grid = a.nwin;
     const int inner = a.nh * a.d;
     const double mtok = (double)a.nwin * FT;

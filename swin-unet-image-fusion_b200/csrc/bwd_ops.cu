@@ -149,7 +149,7 @@ static int launch_gemm_tn_reduce(const float* G, const float* A, float* Wg, long
     if (bias_grad) SF_TRY(launch_colsum(G, bias_grad, M, N, st));
     if (!Wg) return SF_OK;
     const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
-    long long splits = (148LL * 4 + tiles - 1) / tiles;
+    long long splits = ((long long)sm_count() * 4 + tiles - 1) / tiles;
     long long max_splits = (M + 255) / 256;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -201,7 +201,7 @@ static int launch_colsum(const float* G, float* out, long long M, int N, cudaStr
     if (N <= 256) {
         const int threads = (256 / N) * N;              // a multiple of the row length: e0 and the stride keep columns fixed
         const long long total = M * N;
-        long long blocks = 148LL * 8;
+        long long blocks = (long long)sm_count() * 8;
         long long epb = (total + blocks - 1) / blocks;
         epb = (epb + threads - 1) / threads * threads;  // whole block-strides, hence whole rows
         if (epb < 4LL * threads) epb = 4LL * threads;
@@ -210,7 +210,7 @@ static int launch_colsum(const float* G, float* out, long long M, int N, cudaStr
         SF_CHECK_LAUNCH("bwd_colsum");
         return SF_OK;
     }
-    long long blocks = 148LL * 8;
+    long long blocks = (long long)sm_count() * 8;
     if (blocks > (M + 63) / 64) blocks = (M + 63) / 64;
     if (blocks < 1) blocks = 1;
     long long rpb = (M + blocks - 1) / blocks;
@@ -365,7 +365,7 @@ static void launch_ln_bwd_grp(const float* x, const float* gamma, const float* b
     const bool accum = gadd != nullptr;
     const long long rows_per_block = 8 * (32 / G);
     long long blocks = (M + rows_per_block - 1) / rows_per_block;
-    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
     if (eluout) {
         if (accum) k_ln_bwd_grp<G, true, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
         else k_ln_bwd_grp<G, true, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, gy, gx, gadd, ggamma, gbeta, M, C, eps);
@@ -391,18 +391,18 @@ static int launch_ln_bwd(const float* x, const float* gamma, const float* beta, 
     }
     const int threads = 256;
     long long blocks = (M * 32 + threads - 1) / threads;
-    if (blocks > 148LL * 4) blocks = 148LL * 4;
+    if (blocks > (long long)sm_count() * 4) blocks = (long long)sm_count() * 4;
     if (blocks < 1) blocks = 1;
     size_t smem = (size_t)(threads / 32) * 2 * (size_t)C * sizeof(float);
     SF_CHECK_ARG(smem <= 200 * 1024, "LayerNorm backward: row length %d needs %zu B of shared memory", C, smem);
     if (smem > 48 * 1024) {
-        static thread_local bool configured = false;
-        if (!configured) {
+        static DeviceOnce configured;
+        if (configured.need()) {
             cudaFuncSetAttribute(k_ln_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(k_ln_bwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(k_ln_bwd<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(k_ln_bwd<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            configured = true;
+            configured.done();
         }
     }
     ProfScope ps("bwd_layernorm", 20.0 * (double)M * C, 12.0 * (double)M * C, st);
@@ -629,33 +629,33 @@ static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, 
     const int tabn = (2 * g.wsh - 1) * (2 * g.wsw - 1);
     size_t smem = ((size_t)4 * g.T * d + 2 * (size_t)g.T * (g.T + 1) + 2 * tabn + 2) * sizeof(float) + (size_t)g.T * 12 + 16;
     SF_CHECK_ARG(smem <= 200 * 1024, "attention backward: window of %d tokens x head_dim %d needs %zu B of shared memory", g.T, d, smem);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_attn_core_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("attention backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
-        configured = true;
+        configured.done();
     }
     const long long nitems = (long long)g.B * g.nWh * g.nWw * nh;
     int threads = g.T <= 64 ? 64 : (g.T <= 128 ? 128 : 256);
     int per_sm = (int)((200 * 1024) / (smem + 1024));
     if (per_sm > 16) per_sm = 16;
     if (per_sm < 1) per_sm = 1;
-    long long grid = 148LL * per_sm;
+    long long grid = (long long)sm_count() * per_sm;
     if (grid > nitems) grid = nitems;
     const double mtok = (double)g.B * g.Hp * g.Wp;
     ProfScope ps("bwd_attn_core_f32", 12.0 * g.T * mtok * inner, 28.0 * mtok * inner, st);
     if (g.wsh == 7 && g.wsw == 7) {
         const size_t smem7 = ((size_t)4 * 49 * d + 2 * 49 * 51 + 169 + 2) * sizeof(float) + 49 * 12 + 16;
-        static thread_local bool configured7 = false;
-        if (!configured7) {
+        static DeviceOnce configured7;
+        if (configured7.need()) {
             cudaError_t e = cudaFuncSetAttribute(k_attn_core_bwd_w7, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) { set_error("attention backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
-            configured7 = true;
+            configured7.done();
         }
         int psm = (int)((200 * 1024) / (smem7 + 1024));
         if (psm > 16) psm = 16;
         if (psm < 1) psm = 1;
-        long long grid7 = 148LL * psm;
+        long long grid7 = (long long)sm_count() * psm;
         if (grid7 > nitems) grid7 = nitems;
         k_attn_core_bwd_w7<<<(unsigned)grid7, 64, smem7, st>>>(Q, K, V, gO, dQ, dK, dV, table, gtable, g, inner, nh, d, 1.0f / sqrtf((float)d), nitems);
         SF_CHECK_LAUNCH("bwd_attn_core");
@@ -1041,7 +1041,7 @@ int head_bwd(const sf_head_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaSt
     float* vec = ws.take<float>(16);
     if (!t || !vec) { set_error("sf_head_bwd: workspace too small (%zu B given)", ws_bytes); return SF_ERR_WORKSPACE; }
     long long nb = (total + HB_THREADS - 1) / HB_THREADS;
-    if (nb > 148LL * 8) nb = 148LL * 8;
+    if (nb > (long long)sm_count() * 8) nb = (long long)sm_count() * 8;
     const int blocks = (int)nb;
     ProfScope ps("bwd_final_head", 200.0 * (double)total, 60.0 * (double)total, st);
     k_hb_prepare<<<1, 32, 0, st>>>(p->bn_gamma, p->bn_beta, p->running_mean, p->running_var, p->save_mean, p->save_invstd, vec, p->bn_eps, p->training);

@@ -12,7 +12,7 @@ namespace sf {
 static constexpr int kCT = 256;
 static inline int color_grid(long long n) {
     long long b = (n + kCT - 1) / kCT;
-    const long long cap = 148LL * 16;
+    const long long cap = (long long)sm_count() * 16;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;

@@ -50,6 +50,17 @@ struct ProfScope {
         if (rc__ != SF_OK) return rc__; \
     } while (0)
 
+// SMs of the current device (148 on B200), cached per device: persistent grids are sized in multiples of it
+int sm_count();
+// One-time per-DEVICE set-up (cudaFuncSetAttribute is per context, not per host thread): a static instance per call
+// site remembers which devices have been configured.  A race between two host threads only repeats the cheap call.
+struct DeviceOnce {
+    unsigned long long mask = 0;
+    int dev = 0;
+    bool need() { cudaGetDevice(&dev); return !((mask >> (dev & 63)) & 1ull); }
+    void done() { mask |= 1ull << (dev & 63); }
+};
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

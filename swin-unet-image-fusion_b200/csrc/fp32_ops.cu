@@ -113,7 +113,7 @@ template <int NF4>
 static void launch_ln_small(const float* in, const float* gamma, const float* beta, float* out, long long M, int C, float eps,
                             int act, const UnmergeGeom* ug, cudaStream_t st) {
     long long blocks = (M + 127) / 128;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
     UnmergeGeom g = ug ? *ug : UnmergeGeom{0, 0, 0, 0, 0};
     if (ug) {
         if (act) k_ln_rows_small<true, true, NF4><<<(int)blocks, 128, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
@@ -128,7 +128,7 @@ int launch_layernorm(const float* in, const float* gamma, const float* beta, flo
                      int act, const UnmergeGeom* ug, cudaStream_t st) {
     const int threads = 256;
     long long blocks = (M * 32 + threads - 1) / threads;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     if (blocks < 1) blocks = 1;
     UnmergeGeom g = ug ? *ug : UnmergeGeom{0, 0, 0, 0, 0};
     ProfScope ps(act ? "layernorm_elu" : "layernorm", 8.0 * (double)M * C, 8.0 * (double)M * C, st);
@@ -498,7 +498,7 @@ __global__ void k_head_conv2(const float2* __restrict__ t, const float* __restri
 
 static int head_blocks(long long total) {
     long long blocks = (total + HEAD_THREADS - 1) / HEAD_THREADS;
-    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
     return (int)(blocks < 1 ? 1 : blocks);
 }
 

@@ -297,7 +297,7 @@ int gemm_tf32_nt(const GemmBatch& batch, int nbatch, long long M, int N, int K, 
 int gemm_tf32_wgrad(const float* G, const float* A, float* Wg, float* bias_grad, long long M, int N, int K, bool elu_a, cudaStream_t st) {
     SF_CHECK_ARG(Wg, "gemm_tf32_wgrad: null weight gradient");
     const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
-    long long splits = (148LL * 4 + tiles - 1) / tiles;
+    long long splits = ((long long)sm_count() * 4 + tiles - 1) / tiles;
     long long max_splits = (M + 255) / 256;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -12,7 +12,7 @@ static constexpr int kThreads = 256;
 static inline int grid_for(long long work_items) {
     // persistent-ish grid: enough CTAs to fill 148 SMs x 8 resident CTAs, grid-stride inside
     long long blocks = (work_items + kThreads - 1) / kThreads;
-    const long long cap = 148LL * 16;
+    const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;

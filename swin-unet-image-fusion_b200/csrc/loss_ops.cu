@@ -449,7 +449,7 @@ extern "C" int sf_scale_by_scalar(const float* in, const float* scalar, float* o
     using namespace sf;
     SF_CHECK_ARG(in && scalar && out && n > 0, "sf_scale_by_scalar: null pointer or empty tensor");
     long long b = (n + 255) / 256;
-    if (b > 148LL * 8) b = 148LL * 8;
+    if (b > (long long)sm_count() * 8) b = (long long)sm_count() * 8;
     ProfScope ps("scale_by_scalar", 0.0, 8.0 * n, as_stream(stream));
     k_scale_by_scalar<<<(unsigned)b, 256, 0, as_stream(stream)>>>(in, scalar, out, n);
     SF_CHECK_LAUNCH("sf_scale_by_scalar");

@@ -82,7 +82,7 @@ int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float
                 int k_chunks, cudaStream_t st) {
     long long total = (long long)NR * KR / 8 * n_chunks * k_chunks;
     int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     if (blocks < 1) blocks = 1;
     ProfScope ps("pack_weights_bf16", 0.0, 6.0 * (double)nsrc * Neach * K, st);
     k_pack_w<<<blocks, 256, 0, st>>>(src, nsrc, Neach, K, out, bias_out, NR, KR, n_chunks, k_chunks);
@@ -150,7 +150,7 @@ int launch_pack_mapped(const PackSrc& src, const PackMap& map, int K, bf16* out,
                        int k_chunks, cudaStream_t st) {
     long long total = (long long)NR * KR / 8 * n_chunks * k_chunks;
     int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     if (blocks < 1) blocks = 1;
     double rows = 0;
     for (int s = 0; s < map.nsrc; s++) rows += map.rows[s];
@@ -438,7 +438,7 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
     const int Kpad = (int)pad16((uint32_t)C);
     SF_CHECK_ARG(C % 4 == 0 && Kpad <= TC_MAX_KPAD, "ln_to_tiled: unsupported row width %d", C);
     long long blocks = (M * 32 + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
     if (blocks < 1) blocks = 1;
     ProfScope ps(prof_name("ln_to_tiled_c%d", C), 8.0 * (double)M * C, 6.0 * (double)M * C, st);
     SF_CHECK_ARG(!wo || M < 2147483647LL, "ln_to_tiled: %lld rows exceed the window-order index range", M);
@@ -772,11 +772,11 @@ int tc_gemm_plan(TcGemm* p) {
 template <int AMODE, int OUTMODE>
 static int launch_t(const TcGemm& p, const char* name, cudaStream_t st) {
     GemmSmem L = gemm_smem_layout(p);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm2<AMODE, OUTMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
         if (e != cudaSuccess) { set_error("tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
-        configured = true;
+        configured.done();
     }
     const long long m_tiles = (p.M + 127) / 128;
     const long long items = m_tiles * p.n_groups;
@@ -786,7 +786,7 @@ static int launch_t(const TcGemm& p, const char* name, cudaStream_t st) {
     per_sm = std::min(per_sm, (int)(512u / ncols));
     per_sm = std::min(per_sm, 65536 / (threads * (AMODE == AM_TILED ? 66 : 100)));
     per_sm = std::max(1, std::min(per_sm, 4));
-    long long grid = 148LL * per_sm;
+    long long grid = (long long)sm_count() * per_sm;
     if (grid > items) grid = items;
     const double abytes = (AMODE == AM_TILED ? 2.0 : 4.0) * (double)p.M * p.K;
     const double obytes = (OUTMODE == OUT_F32 ? 4.0 : 2.0) * (double)p.M * p.N + (p.residual ? 4.0 * (double)p.M * p.N : 0.0);

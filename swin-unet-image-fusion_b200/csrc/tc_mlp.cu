@@ -343,14 +343,14 @@ bool tc_mlp_supported(int C, int hidden) {
 int launch_tc_mlp(const TcMlp& t, cudaStream_t st) {
     SF_CHECK_ARG(tc_mlp_supported(t.C, t.hidden), "tc_mlp: unsupported shape C=%d hidden=%d", t.C, t.hidden);
     const MlpSmem L = mlp_smem_layout(t.Cpad, t.Hpad, t.Cpad, t.C, t.max_stages);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM_LIMIT);
         if (e != cudaSuccess) { set_error("tc_mlp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
-        configured = true;
+        configured.done();
     }
     const long long tiles = (t.M + 127) / 128;
-    long long grid = 148;
+    long long grid = sm_count();
     if (grid > tiles) grid = tiles;
     // algorithmic work: two GEMMs; bytes: x in, residual in (when it is another tensor), out, weights once
     ProfScope ps(prof_name("tc_mlp_fused_c%d", t.C), 4.0 * (double)t.M * t.C * t.hidden,

@@ -68,7 +68,7 @@ class WindowAttention(nn.Module):
             raise SwinFuseError("WindowAttention: non-zero dropout is not supported by the fused kernel "
                                 "(the reference config uses 0, A000_CONFIG.py:61-62)")
 
-    def fused(self, q_src, kv_src, ln_q=None, ln_kv=None, residual=None):
+    def fused(self, q_src, kv_src, ln_q=None, ln_kv=None, residual=None, eps: float = 1e-5):
         """LN -> attention -> (+ residual) in one operator call; used by BasicBlock."""
         self._check_dropout()
         self.initialize_feature_shape_hw(q_src)
@@ -78,7 +78,7 @@ class WindowAttention(nn.Module):
             wv=self.v_for_heads.weight, bv=self.v_for_heads.bias, wo=self.linear_projection.weight,
             bo=self.linear_projection.bias, bias_table=self.relative_position_bias_table, num_heads=self.num_heads,
             head_dim=self.dims_per_head, window_size=self.window_size, shift=self.use_cyclic_shift, ln_q=ln_q,
-            ln_kv=ln_kv, residual=residual, precision=self.precision)
+            ln_kv=ln_kv, residual=residual, eps=eps, precision=self.precision)
 
     def forward(self, q, k, v):
         if not _same_tensor(k, v):

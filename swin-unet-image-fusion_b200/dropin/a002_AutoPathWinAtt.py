@@ -26,15 +26,15 @@ class AutoPathWinAtt(nn.Module):
         if use_dual_path:
             self.window_attention_y = make()
 
-    def fused(self, x, y, ln_x, ln_y):
+    def fused(self, x, y, ln_x, ln_y, eps: float = 1e-5):
         """x + Attn_x(LN_x(x), ...), y + Attn_y(LN_y(y), ...) with LN and residual inside the operator."""
         if not self.use_dual_path:
-            return self.window_attention_x.fused(x, None, ln_q=ln_x, ln_kv=ln_x, residual=x)
+            return self.window_attention_x.fused(x, None, ln_q=ln_x, ln_kv=ln_x, residual=x, eps=eps)
         if self.use_cross_att:  # both directions read the pre-update tensors (a002:70-73)
-            return ops.dual_path(lambda: self.window_attention_x.fused(x, y, ln_q=ln_x, ln_kv=ln_y, residual=x),
-                                 lambda: self.window_attention_y.fused(y, x, ln_q=ln_y, ln_kv=ln_x, residual=y))
-        return ops.dual_path(lambda: self.window_attention_x.fused(x, None, ln_q=ln_x, ln_kv=ln_x, residual=x),
-                             lambda: self.window_attention_y.fused(y, None, ln_q=ln_y, ln_kv=ln_y, residual=y))
+            return ops.dual_path(lambda: self.window_attention_x.fused(x, y, ln_q=ln_x, ln_kv=ln_y, residual=x, eps=eps),
+                                 lambda: self.window_attention_y.fused(y, x, ln_q=ln_y, ln_kv=ln_x, residual=y, eps=eps))
+        return ops.dual_path(lambda: self.window_attention_x.fused(x, None, ln_q=ln_x, ln_kv=ln_x, residual=x, eps=eps),
+                             lambda: self.window_attention_y.fused(y, None, ln_q=ln_y, ln_kv=ln_y, residual=y, eps=eps))
 
     def forward(self, x, y):
         if not self.use_dual_path:

@@ -33,17 +33,17 @@ class AutoPathMLP(nn.Module):
             setattr(self, f"sequence_{path}", nn.Sequential(fc1, activation_func, d1, fc2, d2))
         self.precision = None
 
-    def fused_path(self, path: str, t, ln=None, residual=None):
+    def fused_path(self, path: str, t, ln=None, residual=None, eps: float = 1e-5):
         if self.training and self.drop_ratio > 0:
             raise SwinFuseError("AutoPathMLP: non-zero dropout is not supported (A000_CONFIG.py:65 uses 0)")
         fc1, fc2 = getattr(self, f"mlp_{path}_1"), getattr(self, f"mlp_{path}_2")
         return ops.mlp(t, w1=fc1.weight, b1=fc1.bias, w2=fc2.weight, b2=fc2.bias, ln=ln, residual=residual,
-                       precision=self.precision)
+                       eps=eps, precision=self.precision)
 
-    def fused(self, x, y, ln_x, ln_y):
+    def fused(self, x, y, ln_x, ln_y, eps: float = 1e-5):
         if self.use_dual_path or y is not None:
-            return ops.dual_path(lambda: self.fused_path("x", x, ln_x, x), lambda: self.fused_path("y", y, ln_y, y))
-        return self.fused_path("x", x, ln_x, x)
+            return ops.dual_path(lambda: self.fused_path("x", x, ln_x, x, eps), lambda: self.fused_path("y", y, ln_y, y, eps))
+        return self.fused_path("x", x, ln_x, x, eps)
 
     def forward(self, x, y):
         if self.use_dual_path or y is not None:

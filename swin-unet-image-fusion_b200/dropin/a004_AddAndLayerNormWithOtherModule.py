@@ -1,6 +1,7 @@
 """Drop-in for a004_AddAndLayerNormWithOtherModule.py: the pre-norm residual wrapper
 ``x + other(LN_C(x))`` (a004:20-48).  When ``other_module`` is one of this package's attention /
 MLP modules, LayerNorm and the residual add are folded into that module's kernel call."""
+import torch
 from torch import nn
 
 from a007_utils import *  # noqa: F401,F403
@@ -23,8 +24,16 @@ class AddAndLayerNormWithOtherModule(nn.Module):
         dual = self.use_dual_path or y is not None
         fused = getattr(self.other_module, "fused", None)
         if fused is not None:
-            return fused(x, y if dual else None, _ln(self.norm_layer_1), _ln(self.norm_layer_2) if dual else None)
-        # generic other_module: forward-only composition of the standalone operators
+            if dual and self.norm_layer_2.eps != self.norm_layer_1.eps:
+                raise ops.SwinFuseError("AddAndLayerNormWithOtherModule: both LayerNorms must share one eps")
+            return fused(x, y if dual else None, _ln(self.norm_layer_1), _ln(self.norm_layer_2) if dual else None,
+                         eps=self.norm_layer_1.eps)
+        # generic other_module: forward-only composition of the standalone operators (sf_layernorm has no adjoint
+        # outside the fused operators): refuse to drop gradients silently
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in
+                                           (x, y, self.norm_layer_1.weight, self.norm_layer_1.bias)):
+            raise ops.SwinFuseError("AddAndLayerNormWithOtherModule: the non-fused composition is forward-only; wrap an "
+                                    "AutoPathWinAtt / AutoPathMLP (fused operators own the gradients) or run under no_grad")
         if dual:
             nx, ny = my_layer_norm(x, self.norm_layer_1, y, self.norm_layer_2)
             ox, oy = self.other_module(nx, ny)
