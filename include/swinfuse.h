@@ -272,9 +272,11 @@ int sf_head_bwd(const sf_head_bwd_params* p, void* workspace, size_t workspace_b
 
 /* One Adam step (torch.optim.Adam semantics, a016:67: no weight decay, no amsgrad) over flat fp32
  * buffers of n elements: g' = grad * grad_scale (1/world_size after the data-parallel all-reduce);
- * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
-int sf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                 float beta2, float eps, int step, float grad_scale, void* stream);
+ * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * The scalar hyper-parameters are doubles (as the Python optimizer holds them): 1-b, the bias corrections and the
+ * step size are formed in double and rounded to fp32 once, which is what makes the result match torch to 1e-6. */
+int sf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+                 double beta2, double eps, int step, double grad_scale, void* stream);
 
 /* Fusion loss of a008_loss.py (MyLoss.calcu_total_loss, a008:226-282, constants A000_CONFIG.py:34-52) and its
  * gradient w.r.t. the fused image, SURVEY 8(a) row a19.  fusion / ir / vis: contiguous (B,1,H,W) fp32.

@@ -198,11 +198,12 @@ __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, 
 }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                       float step_size, float b1, float b2, float inv_sqrt_bc2, float eps, float gscale) {
+                       float step_size, float b1, float b2, float omb1, float omb2, float inv_sqrt_bc2, float eps, float gscale) {
+    // omb1 / omb2 = 1 - beta, formed in double on the host as torch.optim.Adam does (1 - 0.999f in float is off by 5e-5 relative)
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
-        float mi = b1 * m[i] + (1.f - b1) * gi;
-        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        float mi = b1 * m[i] + omb1 * gi;
+        float vi = b2 * v[i] + omb2 * gi * gi;
         m[i] = mi;
         v[i] = vi;
         p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
@@ -386,13 +387,15 @@ int sf_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, voi
     return transpose_launch("sf_nhwc_to_nchw", in, out, B, H * W, C, stream);
 }
 
-int sf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
-                 float eps, int step, float grad_scale, void* stream) {
+int sf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1, double beta2,
+                 double eps, int step, double grad_scale, void* stream) {
     SF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "sf_adam_step: bad args");
-    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    // scalars arrive and are combined in double, as torch.optim.Adam forms them in Python, and are rounded to fp32 once
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
     ProfScope ps("adam_step", 12.0 * (double)n, 28.0 * (double)n, as_stream(stream));
-    k_adam<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), beta1, beta2,
-                                                             (float)(1.0 / sqrt(bc2)), eps, grad_scale);
+    k_adam<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), (float)beta1, (float)beta2,
+                                                             (float)(1.0 - beta1), (float)(1.0 - beta2), (float)(1.0 / sqrt(bc2)), (float)eps,
+                                                             (float)grad_scale);
     SF_CHECK_LAUNCH("sf_adam_step");
     return SF_OK;
 }

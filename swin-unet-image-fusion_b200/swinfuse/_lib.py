@@ -81,7 +81,7 @@ class ProfileEntry(C.Structure):
                 ("bytes", C.c_double)]
 
 
-_i, _ll, _fl, _sz = C.c_int, C.c_longlong, C.c_float, C.c_size_t
+_i, _ll, _fl, _sz, _d = C.c_int, C.c_longlong, C.c_float, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes): every symbol include/swinfuse.h declares
 SIGNATURES = {
@@ -132,7 +132,7 @@ SIGNATURES = {
     "sf_fusion_loss_workspace_bytes": (_sz, [C.POINTER(FusionLossParams)]),
     "sf_fusion_loss": (_i, [C.POINTER(FusionLossParams), _f, _sz, _f]),
     "sf_scale_by_scalar": (_i, [_f, _f, _f, _ll, _f]),
-    "sf_adam_step": (_i, [_f, _f, _f, _f, _ll, _fl, _fl, _fl, _fl, _i, _fl, _f]),
+    "sf_adam_step": (_i, [_f, _f, _f, _f, _ll, _d, _d, _d, _d, _i, _d, _f]),
 }
 
 _lib = None
