@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 #include "bf16_kernels.cuh"
 #include "tc_common.cuh"
+#include "hmma_util.cuh"
 
 namespace sf {
 
@@ -45,39 +46,6 @@ struct AttnFragArgs {
     int nwin;
     FastDiv dnW, dnWw;
 };
-
-__device__ __forceinline__ float ex2f(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcpf(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float max3f(float a, float b, float c) {
-    float y;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
-    return y;
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// 8x8 b16 transpose across the warp: in: lane (gq, tq) holds M[gq][2tq..2tq+1]; out: M[2tq..2tq+1][gq]
-__device__ __forceinline__ uint32_t movm_trans(uint32_t x) {
-    uint32_t y;
-    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
-    return y;
-}
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint2 ldg64(const __half* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
-__device__ __forceinline__ uint32_t ldg32(const __half* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 
 // operand fragments of one (window, head) for one slab, as loaded (V still row-major)
 template <int KSTEPS, int NDT>

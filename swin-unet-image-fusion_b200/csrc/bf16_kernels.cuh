@@ -109,4 +109,11 @@ int launch_attn_core_bf16(const bf16* qkv, int qkv_fp16, long long ld, int koff,
 bool attn_frag_supported(const WinGeom& g, int nh, int d);
 int launch_attn_frag(const __half* qkv, int ld, bf16* O, const float* table, const WinGeom& g, int nh, int d, cudaStream_t st);
 
+// Fused window-attention operator for C <= 64, 8 heads, 7x7 windows (wa_fused.cu): LayerNorm, q|k|v projection (tcgen05),
+// attention core (HMMA), output projection (tcgen05), bias + residual, window gather / scatter -- one persistent kernel.
+// Weight images and biases are the ones window_attn_pack_bf16 writes for the 7x7 (frag) plan.
+bool wa_fused_supported(const WinGeom& g, int C, int nh, int d);
+int launch_wa_fused(const sf_window_attn_params* p, const WinGeom& g, bool self_attn, const bf16* Wq, const float* bq, const bf16* Wkv,
+                    const float* bkv, const bf16* Wo, const float* bo, cudaStream_t st);
+
 }  // namespace sf

@@ -47,6 +47,7 @@ static void bind_packed(TcGemm& t, const PackedGemm& g, const char* packed_base)
 struct WaPlan {
     bool self_attn;
     bool frag;                    // 7x7 windows: window-order GEMMs + HMMA attention core (attn_frag.cu)
+    bool fused;                   // narrow stages (C <= 64): the whole operator is ONE kernel (wa_fused.cu), nothing staged in HBM
     int inner, dp, hw;            // frag: padded head width of the q / k / v / O columns, hw = heads * dp
     WinGeom geom;
     PackedGemm q, kv, o;          // q: stacked q|k|v for self attention
@@ -62,6 +63,7 @@ static WaPlan wa_plan(const sf_window_attn_params* p) {
     w.inner = p->num_heads * p->head_dim;
     w.geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
     w.frag = attn_frag_supported(w.geom, p->num_heads, p->head_dim) && M < 2147483647LL / 64;
+    w.fused = w.frag && wa_fused_supported(w.geom, p->C, p->num_heads, p->head_dim);
     w.dp = qkvh_dp(p->head_dim);
     w.hw = p->num_heads * w.dp;
     Carver pc;
@@ -76,8 +78,8 @@ static WaPlan wa_plan(const sf_window_attn_params* p) {
     w.packed_bytes = pc.off;
     Carver c;
     const int ocols = w.frag ? w.hw : w.inner;   // columns of q, k, v and O rows
-    w.off_qkv = c.take(tiled_elems(M, 3 * ocols) * sizeof(bf16));   // fp16 rows
-    w.off_o = c.take(tiled_elems(M, ocols) * sizeof(bf16));
+    w.off_qkv = c.take(w.fused ? 0 : tiled_elems(M, 3 * ocols) * sizeof(bf16));   // fp16 rows
+    w.off_o = c.take(w.fused ? 0 : tiled_elems(M, ocols) * sizeof(bf16));
     w.off_packed = c.take(p->packed ? 0 : w.packed_bytes);
     w.prepass_q = p->ln_q_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
     w.prepass_kv = !w.self_attn && p->ln_kv_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
@@ -145,7 +147,7 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
     SF_TRY(wa_check(p));
     const WaPlan w = wa_plan(p);
     const int inner = w.inner, C = p->C;
-    if (ws_bytes < w.total || !ws_ptr) { set_error("sf_window_attn_fwd: workspace too small (%zu B given, %zu needed)", ws_bytes, w.total); return SF_ERR_WORKSPACE; }
+    if (ws_bytes < w.total || (w.total && !ws_ptr)) { set_error("sf_window_attn_fwd: workspace too small (%zu B given, %zu needed)", ws_bytes, w.total); return SF_ERR_WORKSPACE; }
     char* base = reinterpret_cast<char*>(ws_ptr);
     const long long M = (long long)p->B * p->Hp * p->Wp;
     bf16* qkv = reinterpret_cast<bf16*>(base + w.off_qkv);
@@ -154,6 +156,13 @@ int window_attn_fwd_bf16(const sf_window_attn_params* p, void* ws_ptr, size_t ws
     if (!pk) {
         SF_TRY(window_attn_pack_bf16(p, base + w.off_packed, w.packed_bytes, st));
         pk = base + w.off_packed;
+    }
+    if (w.fused) {
+        // LN -> q|k|v projection -> attention core -> output projection -> + residual, scattered back: one kernel
+        const bf16* Wkv = w.self_attn ? nullptr : reinterpret_cast<const bf16*>(pk + w.kv.off_w);
+        const float* bkv = w.self_attn ? nullptr : reinterpret_cast<const float*>(pk + w.kv.off_b);
+        return launch_wa_fused(p, w.geom, w.self_attn, reinterpret_cast<const bf16*>(pk + w.q.off_w), reinterpret_cast<const float*>(pk + w.q.off_b),
+                               Wkv, bkv, reinterpret_cast<const bf16*>(pk + w.o.off_w), reinterpret_cast<const float*>(pk + w.o.off_b), st);
     }
     // projections -> q|k|v (fp16).  7x7 windows: the GEMMs run on rows in window order (A producers gather, shift and
     // partition as index math) and write per-(window, head) blobs for the HMMA core; otherwise plain fp16 rows.

@@ -227,3 +227,77 @@ def test_unsupported_shapes_raise_not_fallback():
     with pytest.raises(sw.SwinFuseError):
         sw.ops.mlp(x, w1=torch.randn(8, 6, 1, 1, device="cuda"), b1=torch.zeros(8, device="cuda"),
                    w2=torch.randn(6, 8, 1, 1, device="cuda"), b2=torch.zeros(6, device="cuda"), precision="bf16")
+
+
+def _wa_problem(c, nh, d, b, hp, wp, seed):
+    g = torch.Generator().manual_seed(seed)
+    x, y = torch.randn(b, c, hp, wp, generator=g), torch.randn(b, c, hp, wp, generator=g)
+    s = (1.0 / c) ** 0.5
+    p = {"q_for_heads.weight": torch.randn(nh * d, c, generator=g) * s, "q_for_heads.bias": torch.randn(nh * d, generator=g) * 0.1,
+         "k_for_heads.weight": torch.randn(nh * d, c, generator=g) * s, "k_for_heads.bias": torch.randn(nh * d, generator=g) * 0.1,
+         "v_for_heads.weight": torch.randn(nh * d, c, generator=g) * s, "v_for_heads.bias": torch.randn(nh * d, generator=g) * 0.1,
+         "linear_projection.weight": torch.randn(c, nh * d, generator=g) * s, "linear_projection.bias": torch.randn(c, generator=g) * 0.1,
+         "relative_position_bias_table": torch.randn(13, 13, generator=g)}
+    ln = [(1 + 0.2 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)) for _ in range(2)]
+    return x, y, p, ln
+
+
+def _wa_call(sw, x, y, p, nh, d, shift, ln_q, ln_kv, residual):
+    cu = {k: v.cuda() for k, v in p.items()}
+    dev = lambda t: None if t is None else (tuple(u.cuda() for u in t) if isinstance(t, tuple) else t.cuda())   # noqa: E731
+    return sw.ops.window_attention(
+        x.cuda(), dev(y), wq=cu["q_for_heads.weight"], bq=cu["q_for_heads.bias"], wk=cu["k_for_heads.weight"],
+        bk=cu["k_for_heads.bias"], wv=cu["v_for_heads.weight"], bv=cu["v_for_heads.bias"], wo=cu["linear_projection.weight"],
+        bo=cu["linear_projection.bias"], bias_table=cu["relative_position_bias_table"], num_heads=nh, head_dim=d,
+        window_size=(7, 7), shift=shift, ln_q=dev(ln_q), ln_kv=dev(ln_kv), residual=dev(residual), precision="bf16")
+
+
+@pytest.mark.parametrize("c,d,b,hp,wp", [
+    (24, 3, 1, 21, 21),     # 9 windows: odd count, the last tile holds one window
+    (24, 3, 3, 133, 133),   # 1,083 windows on <= 296 CTAs: several tiles per CTA (mbarrier phases wrap), odd tail
+    (48, 6, 1, 35, 21),     # 15 windows, 16-byte heads
+    (48, 6, 2, 70, 70),     # stage-1 shape of the model
+    (16, 2, 2, 14, 28), (8, 1, 1, 7, 14), (40, 5, 1, 14, 14), (56, 7, 2, 21, 7)])   # every head width the fused kernel takes
+@pytest.mark.parametrize("shift", [False, True])
+@pytest.mark.parametrize("cross", [False, True])
+def test_fused_window_attention_kernel_vs_oracle(c, d, b, hp, wp, shift, cross):
+    """wa_fused.cu (one kernel: LN -> q|k|v -> attention -> projection -> + residual, C <= 64, 8 heads): every
+    (self | cross) x (plain | shifted) combination against the CPU oracle (a001:448-474 + a004:29-38), incl. ragged tiles."""
+    sw = dropin()
+    nh = 8
+    x, y, p, ln = _wa_problem(c, nh, d, b, hp, wp, seed=1000 * c + 10 * hp + 2 * int(shift) + int(cross))
+    qn = fo.layer_norm_c(x, *ln[0])
+    kvn = fo.layer_norm_c(y, *ln[1]) if cross else qn
+    ref = x + fo.window_attention(qn, kvn, p, "", nh, d, (7, 7), shift)
+    got = _wa_call(sw, x, y if cross else None, p, nh, d, shift, ln[0], ln[1] if cross else ln[0], x)
+    assert rel_err(got, ref) <= TOL_BF16, rel_err(got, ref)
+    assert rel_l2(got, ref) <= 5e-3, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("c,d", [(24, 3), (48, 6)])
+def test_fused_window_attention_without_layernorm_and_with_foreign_residual(c, d):
+    """WindowAttention.forward called directly (a001:448-474: no pre-norm, no residual) and with a residual tensor that is
+    neither source -- the operator's optional inputs."""
+    sw = dropin()
+    nh = 8
+    x, y, p, _ = _wa_problem(c, nh, d, 2, 28, 21, seed=77 + c)
+    other = torch.randn(x.shape, generator=torch.Generator().manual_seed(5))
+    ref = fo.window_attention(x, y, p, "", nh, d, (7, 7), True)
+    got = _wa_call(sw, x, y, p, nh, d, True, None, None, None)
+    assert rel_err(got, ref) <= TOL_BF16, rel_err(got, ref)
+    got = _wa_call(sw, x, y, p, nh, d, True, None, None, other)
+    assert rel_err(got, ref + other) <= TOL_BF16, rel_err(got, ref + other)
+
+
+def test_fused_window_attention_is_deterministic_and_batch_invariant():
+    """No atomics, no cross-CTA reduction: two runs are bit-identical and a batch equals its samples run one by one
+    (tiles straddle the samples: 25 windows per sample, two windows per tile)."""
+    sw = dropin()
+    nh, c, d = 8, 24, 3
+    x, y, p, ln = _wa_problem(c, nh, d, 4, 35, 35, seed=3)
+    a = _wa_call(sw, x, y, p, nh, d, True, ln[0], ln[1], x)
+    b = _wa_call(sw, x, y, p, nh, d, True, ln[0], ln[1], x)
+    assert torch.equal(a, b)
+    for i in range(4):
+        one = _wa_call(sw, x[i:i + 1], y[i:i + 1], p, nh, d, True, ln[0], ln[1], x[i:i + 1])
+        assert torch.equal(one[0], a[i])
