@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sf {
 using bf16 = __nv_bfloat16;
@@ -31,7 +32,7 @@ int patch_pack_bf16(const sf_patch_params* p, void* packed, size_t bytes, cudaSt
 // zero-padded fp32 bias [n_chunks*NR].
 struct PackSrc { const float* w[3]; const float* b[3]; };
 int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
-                int k_chunks, cudaStream_t st);
+                int k_chunks, cudaStream_t st, int transposed = 0);
 // Same images, but the N axis is a concatenation of sources with their own layout: source s has
 // rows[s] packed rows; head_padded[s] != 0 means packed row n' = h*dp + dd maps to source row h*d + dd
 // (zero when dd >= d); weights and bias of source s are multiplied by scale[s].
@@ -67,6 +68,8 @@ struct TcGemm {
     void* out; long long ldo; int out_col0; int N;
     int out_nkc;              // OUT_TILED: k-chunks per tile of the destination (= pad16(total columns)/8)
     int Hf, Wf, Cin, mh, mw;  // AM_MERGE: fine map (B,Hf,Wf,Cin) and merging factors
+    const bf16* elu_aux;      // OUT_TILED: multiply by ELU'(pre) derived from this saved activation ELU(pre), same tiled layout as out
+    int zero_tail;            // OUT_TILED: rows M .. end of the last tile are written as zeros
     int win_order;            // GEMM rows are in window order: fp32 A producers gather source rows, OUT_F32 scatters rows
     WinOrder wo;
     // ---- tc_gemm_plan fills ----
@@ -81,6 +84,37 @@ int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st);
 int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st,
                        const WinOrder* wo = nullptr);
 static constexpr int TC_LN_PREPASS_MIN_C = 96;   // rows at least this wide are normalised by the pre-pass
+
+// ---- workspace carving and packed-weight plans shared by the operator implementations (bf16_path.cu, tc_bwd.cu) ----
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline size_t tiled_elems(long long M, int cols) { return (size_t)((M + 127) / 128) * 128 * tc::pad16((uint32_t)cols); }
+
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off += align_up(bytes); return o; }
+};
+
+// plan of one GEMM's packed weights: bf16 images + padded fp32 bias inside the packed buffer
+struct PackedGemm { int nch, nc, kpad, ks, nslabs; size_t off_w, off_b; };
+
+static inline PackedGemm plan_packed(Carver& c, int N, int K) {
+    PackedGemm g{};
+    tc_gemm_pick_nchunk(N, &g.nch, &g.nc);
+    g.kpad = (int)tc::pad16((uint32_t)K);
+    g.ks = tc_gemm_pick_ks(g.kpad);
+    g.nslabs = g.kpad / g.ks;
+    g.off_w = c.take((size_t)g.nc * g.nch * g.kpad * sizeof(bf16));
+    g.off_b = c.take((size_t)g.nc * g.nch * sizeof(float));
+    return g;
+}
+
+static inline void bind_packed(TcGemm& t, const PackedGemm& g, const char* packed_base) {
+    t.Wp = reinterpret_cast<const bf16*>(packed_base + g.off_w);
+    t.bias = reinterpret_cast<const float*>(packed_base + g.off_b);
+    t.NCH = g.nch;
+    t.n_chunks = g.nc;
+}
+
 
 // ---- fused small-channel MLP (tc_mlp.cu) -------------------------------------------------------------
 // Persistent kernel with both weight matrices resident in shared memory; the hidden activation stays on chip.
@@ -115,5 +149,9 @@ int launch_attn_frag(const __half* qkv, int ld, bf16* O, const float* table, con
 bool wa_fused_supported(const WinGeom& g, int C, int nh, int d);
 int launch_wa_fused(const sf_window_attn_params* p, const WinGeom& g, bool self_attn, const bf16* Wq, const float* bq, const bf16* Wkv,
                     const float* bkv, const bf16* Wo, const float* bo, cudaStream_t st);
+
+// ---- backward pass on tcgen05 (tc_wgrad.cu, tc_bwd.cu) -----------------------------------------------------------------
+// Wg[N][K] += G^T A,  bias_grad[N] += column sums of G;  G: [M x N], A: [M x K], both bf16 UMMA-tiled with zero tail rows
+int launch_tc_wgrad(const bf16* G, const bf16* A, float* Wg, float* bias_grad, long long M, int N, int K, const char* name, cudaStream_t st);
 
 }  // namespace sf

@@ -11,35 +11,6 @@
 namespace sf {
 using namespace tc;
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-static size_t tiled_elems(long long M, int cols) { return (size_t)((M + 127) / 128) * 128 * pad16((uint32_t)cols); }
-
-struct Carver {
-    size_t off = 0;
-    size_t take(size_t bytes) { size_t o = off; off += align_up(bytes); return o; }
-};
-
-// plan of one GEMM's packed weights: bf16 images + padded fp32 bias inside the packed buffer
-struct PackedGemm { int nch, nc, kpad, ks, nslabs; size_t off_w, off_b; };
-
-static PackedGemm plan_packed(Carver& c, int N, int K) {
-    PackedGemm g{};
-    tc_gemm_pick_nchunk(N, &g.nch, &g.nc);
-    g.kpad = (int)pad16((uint32_t)K);
-    g.ks = tc_gemm_pick_ks(g.kpad);
-    g.nslabs = g.kpad / g.ks;
-    g.off_w = c.take((size_t)g.nc * g.nch * g.kpad * sizeof(bf16));
-    g.off_b = c.take((size_t)g.nc * g.nch * sizeof(float));
-    return g;
-}
-
-static void bind_packed(TcGemm& t, const PackedGemm& g, const char* packed_base) {
-    t.Wp = reinterpret_cast<const bf16*>(packed_base + g.off_w);
-    t.bias = reinterpret_cast<const float*>(packed_base + g.off_b);
-    t.NCH = g.nch;
-    t.n_chunks = g.nc;
-}
-
 // =============================================================================================
 // window attention:  [LN] QKV GEMM (fp16 rows) -> HMMA attention core (bf16, UMMA-tiled O)
 //                    -> output projection GEMM (+bias +residual, fp32 rows)

@@ -7,6 +7,8 @@
 // fp16 tensor-core kernels with fp32 accumulation for SF_PREC_BF16 operators (gemm_tf32.cu,
 // attn_bwd_mma.cu).  Weight / bias / table gradients are ACCUMULATED into caller-zeroed buffers
 // with fp32 atomics; activation gradients are written.
+#include <cstdlib>
+#include "bf16_kernels.cuh"
 #include "bwd_kernels.cuh"
 #include "fp32_kernels.cuh"
 
@@ -666,6 +668,101 @@ static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, 
     return SF_OK;
 }
 
+
+// =============================================================================================
+// SF_PREC_BF16 operators: every backward GEMM on tcgen05
+// =============================================================================================
+// Activations and gradients that feed a GEMM are bf16 tensors in the UMMA-tiled layout (tail rows zero): produced by the
+// LayerNorm / cast pre-pass (k_ln_to_tiled) or by a GEMM epilogue, consumed by bulk copies.  Forward recompute and the
+// data gradients dX = dY W run through k_tc_gemm2 (dX with a TRANSPOSED weight image), the weight gradients
+// dW = dY^T X through k_tc_wgrad (tc_wgrad.cu), accumulation in fp32 (TMEM) throughout.
+static bool bwd_tc_enabled() {
+    static const bool on = [] { const char* e = getenv("SWINFUSE_BWD_TC"); return !(e && e[0] == '0'); }();
+    return on;
+}
+static inline size_t tiled_bytes(long long M, int cols) { return tiled_elems(M, cols) * sizeof(bf16); }
+
+// image of W (rows = output features, as stored) with its bias: the forward GEMM  y = x W^T + b
+static int pack_fwd(const float* W, const float* b, int N, int K, const PackedGemm& g, char* base, cudaStream_t st) {
+    PackSrc s{{W, nullptr, nullptr}, {b, nullptr, nullptr}};
+    return launch_pack(s, 1, N, K, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs, st);
+}
+// image of W^T for W stored [R][Cc]: the data-gradient GEMM  dX[M x Cc] = dY[M x R] W
+static int pack_tr(const float* W, int R, int Cc, const PackedGemm& g, char* base, cudaStream_t st) {
+    PackSrc s{{W, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    return launch_pack(s, 1, Cc, R, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs, st, 1);
+}
+// out = A_tiled[M x K] * image^T:  fp32 rows (optionally accumulated into `out_f32`) or bf16 tiled (optionally x ELU'(aux))
+static int tc_gemm_tiled(const bf16* A, long long M, int K, int N, const PackedGemm& g, const char* pk, bool with_bias, bool elu,
+                         float* out_f32, bool accumulate, bf16* out_tiled, const bf16* elu_aux, const char* name, cudaStream_t st) {
+    TcGemm t{};
+    t.A = A; t.M = M; t.K = K; t.a_mode = AM_TILED;
+    bind_packed(t, g, pk);
+    if (!with_bias) t.bias = nullptr;
+    t.elu = elu ? 1 : 0;
+    t.N = N;
+    if (out_tiled) {
+        t.out_mode = OUT_TILED; t.out = out_tiled; t.out_nkc = (int)tc::pad16((uint32_t)N) / 8; t.elu_aux = elu_aux; t.zero_tail = 1;
+    } else {
+        t.out_mode = OUT_F32; t.out = out_f32; t.ldo = N;
+        if (accumulate) { t.residual = out_f32; t.ldr = N; }
+    }
+    SF_TRY(tc_gemm_plan(&t));
+    return launch_tc_gemm(t, name, st);
+}
+// ---- MLP ------------------------------------------------------------------------------------------------------------------
+struct MlpBwdPlan { PackedGemm w1, w2t, w1t; size_t off_pk, off_n, off_h, off_g, off_gh, off_gn, total; };
+static MlpBwdPlan mlp_bwd_tc_plan(const sf_mlp_params* p) {
+    MlpBwdPlan m{};
+    Carver pc;
+    m.w1 = plan_packed(pc, p->hidden, p->C);      // hpre = n W1^T + b1
+    m.w2t = plan_packed(pc, p->hidden, p->C);     // g_h  = gout W2        (image of W2^T: rows = hidden units, k = output channels)
+    m.w1t = plan_packed(pc, p->C, p->hidden);     // g_n  = g_h W1         (image of W1^T: rows = input channels, k = hidden units)
+    Carver c;
+    m.off_pk = c.take(pc.off);
+    m.off_n = c.take(tiled_bytes(p->M, p->C));
+    m.off_h = c.take(tiled_bytes(p->M, p->hidden));
+    m.off_g = c.take(tiled_bytes(p->M, p->C));
+    m.off_gh = c.take(tiled_bytes(p->M, p->hidden));
+    m.off_gn = c.take((size_t)p->M * p->C * sizeof(float));
+    m.total = c.off;
+    return m;
+}
+static bool mlp_bwd_tc_ok(const sf_mlp_params* p) {
+    return bwd_tc_enabled() && p->C % 4 == 0 && (int)tc::pad16((uint32_t)p->C) <= TC_MAX_KPAD && p->hidden % 4 == 0 &&
+           aligned16(p->in) && p->M < 2147483647LL;
+}
+static int mlp_bwd_tc(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const sf_mlp_params* p = &bp->fwd;
+    const long long M = p->M;
+    const int C = p->C, H = p->hidden;
+    const MlpBwdPlan m = mlp_bwd_tc_plan(p);
+    if (ws_bytes < m.total || !ws_ptr) { set_error("sf_mlp_bwd: workspace too small (%zu B given, %zu needed)", ws_bytes, m.total); return SF_ERR_WORKSPACE; }
+    char* base = reinterpret_cast<char*>(ws_ptr);
+    char* pk = base + m.off_pk;
+    bf16* n_t = reinterpret_cast<bf16*>(base + m.off_n);
+    bf16* h_t = reinterpret_cast<bf16*>(base + m.off_h);
+    bf16* g_t = reinterpret_cast<bf16*>(base + m.off_g);
+    bf16* gh_t = reinterpret_cast<bf16*>(base + m.off_gh);
+    float* gn = reinterpret_cast<float*>(base + m.off_gn);
+    SF_TRY(pack_fwd(p->w1, p->b1, H, C, m.w1, pk, st));
+    SF_TRY(pack_tr(p->w2, C, H, m.w2t, pk, st));
+    SF_TRY(pack_tr(p->w1, H, C, m.w1t, pk, st));
+    // recompute: n = LN(x) (or x), a = ELU(n W1^T + b1), both kept as bf16 tiles
+    SF_TRY(launch_ln_to_tiled(p->in, p->ln_gamma, p->ln_beta, n_t, M, C, p->ln_eps, st));
+    SF_TRY(tc_gemm_tiled(n_t, M, C, H, m.w1, pk, true, true, nullptr, false, h_t, nullptr, "bwd_tc_recompute_mlp1", st));
+    SF_TRY(launch_ln_to_tiled(bp->gout, nullptr, nullptr, g_t, M, C, 0.f, st));
+    // g_h = (gout W2) o ELU'(pre), ELU' read off a
+    SF_TRY(tc_gemm_tiled(g_t, M, C, H, m.w2t, pk, false, false, nullptr, false, gh_t, h_t, "bwd_tc_dx_mlp2", st));
+    SF_TRY(launch_tc_wgrad(g_t, h_t, bp->g_w2, bp->g_b2, M, C, H, "bwd_tc_wgrad", st));      // gW2 = gout^T a, gb2
+    SF_TRY(launch_tc_wgrad(gh_t, n_t, bp->g_w1, bp->g_b1, M, H, C, "bwd_tc_wgrad", st));    // gW1 = g_h^T n, gb1
+    float* gdst = p->ln_gamma ? gn : bp->g_in;
+    SF_TRY(tc_gemm_tiled(gh_t, M, H, C, m.w1t, pk, false, false, gdst, false, nullptr, nullptr, "bwd_tc_dx_mlp1", st));
+    if (p->ln_gamma) SF_TRY(launch_ln_bwd(p->in, p->ln_gamma, p->ln_beta, gn, bp->g_in, bp->g_ln_gamma, bp->g_ln_beta, M, C, p->ln_eps, false, bp->add_to_g_in, st));
+    else if (bp->add_to_g_in) SF_TRY(sf_add(bp->g_in, bp->add_to_g_in, bp->g_in, M * C, (void*)st));
+    return SF_OK;
+}
+
 // =============================================================================================
 // operator backward: window attention
 // =============================================================================================
@@ -765,12 +862,14 @@ int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws
 // =============================================================================================
 size_t mlp_bwd_ws(const sf_mlp_bwd_params* bp) {
     const sf_mlp_params* p = &bp->fwd;
+    if (p->precision == SF_PREC_BF16 && mlp_bwd_tc_ok(p)) return mlp_bwd_tc_plan(p).total;
     return 2 * align_up((size_t)p->M * p->hidden * sizeof(float)) + 2 * align_up((size_t)p->M * p->C * sizeof(float));
 }
 
 int mlp_bwd(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
-    const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: TF32 tensor-core GEMMs in the backward pass
+    const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: tensor-core GEMMs in the backward pass
     const sf_mlp_params* p = &bp->fwd;
+    if (tf && mlp_bwd_tc_ok(p)) return mlp_bwd_tc(bp, ws_ptr, ws_bytes, st);
     const long long M = p->M;
     const int C = p->C, H = p->hidden;
     Workspace ws(ws_ptr, ws_bytes);

@@ -40,8 +40,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // =============================================================================================
 // weight packing
 // =============================================================================================
+// tr != 0: the (single) source is stored [K][Neach] row-major and the image is that of its transpose
+// (out[n][k] = src[k][n]): the packed W^T of the backward data-gradient GEMMs dX = dY W.
 __global__ void k_pack_w(PackSrc src, int nsrc, int Neach, int K, bf16* __restrict__ out, float* __restrict__ bias_out,
-                         int NR, int KR, int n_chunks, int k_chunks) {
+                         int NR, int KR, int n_chunks, int k_chunks, int tr) {
     const int Ntot = nsrc * Neach;
     const long long cpi = (long long)NR * KR / 8;  // 16-byte chunks per image
     const long long total = cpi * n_chunks * k_chunks;
@@ -59,7 +61,7 @@ __global__ void k_pack_w(PackSrc src, int nsrc, int Neach, int K, bf16* __restri
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 int k = jk * KR + kc * 8 + e;
-                v[e] = k < K ? row[k] : 0.f;
+                v[e] = k < K ? (tr ? src.w[0][(long long)k * Neach + n] : row[k]) : 0.f;
             }
 #pragma unroll
             for (int e = 0; e < 4; e++) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
@@ -79,13 +81,14 @@ __global__ void k_pack_w(PackSrc src, int nsrc, int Neach, int K, bf16* __restri
 }
 
 int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
-                int k_chunks, cudaStream_t st) {
+                int k_chunks, cudaStream_t st, int transposed) {
+    SF_CHECK_ARG(!transposed || nsrc == 1, "pack: the transposed form takes one source");
     long long total = (long long)NR * KR / 8 * n_chunks * k_chunks;
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     if (blocks < 1) blocks = 1;
     ProfScope ps("pack_weights_bf16", 0.0, 6.0 * (double)nsrc * Neach * K, st);
-    k_pack_w<<<blocks, 256, 0, st>>>(src, nsrc, Neach, K, out, bias_out, NR, KR, n_chunks, k_chunks);
+    k_pack_w<<<blocks, 256, 0, st>>>(src, nsrc, Neach, K, out, bias_out, NR, KR, n_chunks, k_chunks, transposed);
     SF_CHECK_LAUNCH("pack_weights_bf16");
     return SF_OK;
 }
@@ -386,35 +389,42 @@ __device__ __forceinline__ void produce_a_merge(uint8_t* sA, const TcGemm& p, lo
 // =============================================================================================
 __global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
                               bf16* __restrict__ out, long long M, int C, int Kpad, float eps, int gather, WinOrder wo) {
+    // gamma == nullptr: no LayerNorm, a plain fp32 -> bf16 cast into the tiled layout (backward pass operands).
+    // Rows M .. 128*ceil(M/128)-1 of the last tile are written as zeros: the weight-gradient GEMM sums over token rows.
     const int lane = threadIdx.x & 31;
     const int nf4 = C >> 2, nslots = Kpad >> 2, nkc = Kpad >> 3;
+    const long long Mpad = (M + 127) / 128 * 128;
     long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (; row < M; row += stride) {
+    for (; row < Mpad; row += stride) {
         float4 v[3];
-        const long long srow = gather ? win_order_token(wo, (uint32_t)row) : row;
+        const bool real = row < M;
+        const long long srow = (gather && real) ? win_order_token(wo, (uint32_t)row) : row;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             int q = lane + 32 * i;
-            v[i] = q < nf4 ? *reinterpret_cast<const float4*>(in + srow * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = (real && q < nf4) ? *reinterpret_cast<const float4*>(in + srow * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float s = 0.f;
+        float mean = 0.f, rstd = 1.f;
+        if (gamma) {
+            float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 3; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            for (int i = 0; i < 3; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s / (float)C;
-        float ss = 0.f;
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            mean = s / (float)C;
+            float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            if (lane + 32 * i < nf4) {
-                float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
-                ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            for (int i = 0; i < 3; i++) {
+                if (lane + 32 * i < nf4) {
+                    float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                    ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                }
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float rstd = rsqrtf(ss / (float)C + eps);
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            rstd = rsqrtf(ss / (float)C + eps);
+        }
         const long long tile = row >> 7;
         const int r = (int)(row & 127);
 #pragma unroll
@@ -422,10 +432,14 @@ __global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restr
             int q = lane + 32 * i;
             if (q < nslots) {
                 uint2 pk = make_uint2(0u, 0u);
-                if (q < nf4) {
-                    float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + q), bb = __ldg(reinterpret_cast<const float4*>(beta) + q);
-                    pk = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
-                                    pack_bf16x2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w));
+                if (real && q < nf4) {
+                    if (gamma) {
+                        float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + q), bb = __ldg(reinterpret_cast<const float4*>(beta) + q);
+                        pk = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
+                                        pack_bf16x2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w));
+                    } else {
+                        pk = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+                    }
                 }
                 *reinterpret_cast<uint2*>(out + ((tile * nkc + (q >> 1)) * 128 + r) * 8 + (q & 1) * 4) = pk;
             }
@@ -440,7 +454,7 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
     long long blocks = (M * 32 + 255) / 256;
     if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
     if (blocks < 1) blocks = 1;
-    ProfScope ps(prof_name("ln_to_tiled_c%d", C), 8.0 * (double)M * C, 6.0 * (double)M * C, st);
+    ProfScope ps(prof_name(gamma ? "ln_to_tiled_c%d" : "cast_to_tiled_c%d", C), gamma ? 8.0 * (double)M * C : 0.0, 6.0 * (double)M * C, st);
     SF_CHECK_ARG(!wo || M < 2147483647LL, "ln_to_tiled: %lld rows exceed the window-order index range", M);
     k_ln_to_tiled<<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
     SF_CHECK_LAUNCH("ln_to_tiled");
@@ -644,6 +658,13 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                     if (n0 >= p.N) break;  // uniform per warp
                     float v[16];
                     tmem_ld16(tlane + (uint32_t)c16, v);
+                    if (OUTMODE == OUT_TILED && m >= p.M && p.zero_tail) {
+                        // rows past M of the last tile: zeros (the weight-gradient GEMM sums over the rows of this tensor)
+                        bf16* o = reinterpret_cast<bf16*>(p.out);
+                        const int kc = (p.out_col0 + n0) >> 3;
+                        *reinterpret_cast<uint4*>(o + (((size_t)tile * p.out_nkc + kc) * 128 + row) * 8) = make_uint4(0u, 0u, 0u, 0u);
+                        if (kc + 1 < p.out_nkc) *reinterpret_cast<uint4*>(o + (((size_t)tile * p.out_nkc + kc + 1) * 128 + row) * 8) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                     if (m < p.M) {
                         if (p.bias) {
 #pragma unroll
@@ -655,6 +676,20 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                         if (p.elu) {
 #pragma unroll
                             for (int i = 0; i < 16; i++) v[i] = elu_fast(v[i]);
+                        }
+                        if (OUTMODE == OUT_TILED && p.elu_aux) {
+                            // backward of ELU: multiply by ELU'(pre) read off the saved activation a = ELU(pre):
+                            // a > 0 -> 1, else e^pre = a + 1   (a003:23, alpha = 1)
+                            const bf16* ax = p.elu_aux + (((size_t)tile * p.out_nkc + ((p.out_col0 + n0) >> 3)) * 128 + row) * 8;
+                            const uint4 a0 = *reinterpret_cast<const uint4*>(ax);
+                            const uint4 a1 = ((p.out_col0 + n0) >> 3) + 1 < p.out_nkc ? *reinterpret_cast<const uint4*>(ax + 1024) : make_uint4(0u, 0u, 0u, 0u);
+                            const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const float lo = __uint_as_float(aw[i] << 16), hi = __uint_as_float(aw[i] & 0xffff0000u);
+                                v[2 * i] *= lo > 0.f ? 1.f : lo + 1.f;
+                                v[2 * i + 1] *= hi > 0.f ? 1.f : hi + 1.f;
+                            }
                         }
                         if (OUTMODE == OUT_TILED) {
                             // chunk (tile, kc, r) at ((tile*out_nkc + kc)*128 + r)*8 elements; columns >= N are zero

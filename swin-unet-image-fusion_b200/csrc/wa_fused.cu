@@ -41,11 +41,13 @@ static constexpr size_t WF_SMEM_LIMIT = 113 * 1024;   // two CTAs per SM
 
 __host__ __device__ static inline uint32_t wf_al(uint32_t v) { return (v + 127u) & ~127u; }
 
-struct WfSmem { uint32_t wq, wkv, wo, bias, a1q, a1kv, a2, qkv, bars, total; };
+struct WfSmem { uint32_t wq, wkv, wo, bias, a1q, a1kv, a2, qkv, raw, raw_stride, bars, total; };
 
-// DP4: heads of d <= 3 dims padded to 4 columns (HW = 32); otherwise padded to 8 (HW = 64)
+// DP4: heads of d <= 3 dims padded to 4 columns (HW = 32); otherwise padded to 8 (HW = 64).
+// raw: DP4 only -- two staging buffers for the fp32 source rows of the next tiles (cp.async prefetch one tile ahead);
+// the 16-byte-head flavour has no room for them next to its 42 KB of q|k|v rows at two CTAs per SM.
 template <bool DP4>
-__host__ __device__ static inline WfSmem wf_layout(int Kpad, int N2, bool self_attn) {
+__host__ __device__ static inline WfSmem wf_layout(int Kpad, int N2, bool self_attn, int C) {
     constexpr uint32_t HW = DP4 ? 32 : 64, NQKV = 3 * HW, PITCH = DP4 ? 208 : 432;
     WfSmem s{};
     uint32_t o = 0;
@@ -58,6 +60,8 @@ __host__ __device__ static inline WfSmem wf_layout(int Kpad, int N2, bool self_a
     s.a1kv = o; o += wf_al(self_attn ? 0u : kc * WF_LBO);
     s.a2 = o;   o += wf_al((HW >> 3) * WF_LBO);
     s.qkv = o;  o += wf_al((uint32_t)WF_ROWS * PITCH);
+    s.raw_stride = DP4 ? (self_attn ? 1u : 2u) * wf_al((uint32_t)WF_ROWS * (uint32_t)C * 4u) : 0u;   // one tile: q rows [+ k/v rows]
+    s.raw = o;  o += 2u * s.raw_stride;
     s.bars = o; o += 64;
     s.total = o;
     return s;
@@ -72,6 +76,7 @@ struct WaFused {
     const float* table;                   // 13 x 13 relative-position bias table
     WinOrder wo;
     int nwin, C, d, Kpad, N2, self_attn;
+    int debug;   // bit 0: skip the attention core (timing experiments only: SWINFUSE_WF_DEBUG)
 };
 
 __device__ __forceinline__ uint2 lds64(const __half* p) { return *reinterpret_cast<const uint2*>(p); }
@@ -80,7 +85,8 @@ __device__ __forceinline__ uint32_t lds32(const __half* p) { return *reinterpret
 // ---- phase A: gather + LayerNorm + bf16 -> UMMA A operand ---------------------------------------------------------
 // LPR lanes per token row, each lane up to four float4 (q4 = l, l + LPR, ...): 16-byte loads, the two lanes of a 32-byte
 // sector sit next to each other.  Rows of a window are 7 runs of 7 contiguous tokens of the source map.
-template <int LPR, bool LN>
+// STAGED: the rows were brought to shared memory by wf_prefetch (row r of the tile at r * C floats).
+template <int LPR, bool LN, bool STAGED>
 __device__ __forceinline__ void wf_produce(uint8_t* sA, const float* __restrict__ src, const float* __restrict__ g,
                                            const float* __restrict__ b, float eps, const WinOrder& wo, uint32_t m0, int nrows,
                                            int C, int tid) {
@@ -91,7 +97,7 @@ __device__ __forceinline__ void wf_produce(uint8_t* sA, const float* __restrict_
         const int item = base + tid;
         const int r = item / LPR, l = item & (LPR - 1);
         const bool ok = r < nrows;
-        const long long tok = ok ? win_order_token(wo, m0 + (uint32_t)r) : 0;
+        const long long tok = STAGED ? (long long)r : (ok ? win_order_token(wo, m0 + (uint32_t)r) : 0);
         const float4* row = reinterpret_cast<const float4*>(src + tok * C);
         float4 v[4];
 #pragma unroll
@@ -138,6 +144,18 @@ __device__ __forceinline__ void wf_produce(uint8_t* sA, const float* __restrict_
                         make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
             }
         }
+    }
+}
+
+// cp.async gather of the token rows of one tile (window order) into a staging buffer: 16 bytes per copy, issued a
+// whole tile ahead so that the HBM latency is spent under the previous tile's attention core
+__device__ __forceinline__ void wf_prefetch(uint8_t* raw, const float* __restrict__ src, const WinOrder& wo, uint32_t m0, int nrows,
+                                            int C, int tid) {
+    const int nf4 = C >> 2;
+    for (int idx = tid; idx < nrows * nf4; idx += WF_THREADS) {
+        const int r = idx / nf4, q4 = idx - r * nf4;
+        const long long tok = win_order_token(wo, m0 + (uint32_t)r);
+        cp_async16(raw + ((uint32_t)r * (uint32_t)C + (uint32_t)q4 * 4u) * 4u, src + tok * C + q4 * 4);
     }
 }
 
@@ -305,11 +323,12 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_wa_fused(WaFused p) {
     constexpr uint32_t PITCH = DP4 ? 208 : 432;   // bytes per fp16 q|k|v row (16-byte multiple, rotates banks row to row)
     constexpr int PH = (int)PITCH / 2;
     constexpr int LPR = DP4 ? 2 : 4;
+    constexpr bool RAW = DP4;                     // staged source rows (cp.async one tile ahead)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gq = lane >> 2, tq = lane & 3;
     const int Kpad = p.Kpad, N2 = p.N2;
     const bool self_attn = p.self_attn != 0;
-    const WfSmem L = wf_layout<DP4>(Kpad, N2, self_attn);
+    const WfSmem L = wf_layout<DP4>(Kpad, N2, self_attn, p.C);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* w_full = bars;
     uint64_t* d1_full = bars + 1;
@@ -358,95 +377,133 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_wa_fused(WaFused p) {
     const int rb = warp & 3, eg = warp >> 2;   // TMEM lane quarter (hardware: warp id % 4) / which half of the columns
     const int row = rb * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(rb * 32) << 16);
+    const uint32_t raw_kv = self_attn ? 0u : L.raw_stride / 2u;   // k/v rows follow the q rows inside a staging buffer
 
-    uint32_t it = 0;
-#pragma unroll 1
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-        const int win0 = t * WF_WIN;
-        const int nw = min(WF_WIN, p.nwin - win0);
-        const int nrows = nw * WF_T;
-        const uint32_t m0row = (uint32_t)win0 * WF_T;
-
-        // ---- A: gather + LayerNorm -> A1 ------------------------------------------------------------------------------
-        if (p.ln_q_g) wf_produce<LPR, true>(smem + L.a1q, p.q_src, p.ln_q_g, p.ln_q_b, p.eps, p.wo, m0row, nrows, p.C, tid);
-        else wf_produce<LPR, false>(smem + L.a1q, p.q_src, nullptr, nullptr, p.eps, p.wo, m0row, nrows, p.C, tid);
+    auto tile_rows = [&](int t) { return min(WF_WIN, p.nwin - t * WF_WIN) * WF_T; };
+    // staged source rows of tile t -> staging buffer `buf` (no wait)
+    auto prefetch = [&](int t, uint32_t buf) {
+        uint8_t* raw = smem + L.raw + buf * L.raw_stride;
+        wf_prefetch(raw, p.q_src, p.wo, (uint32_t)t * WF_ROWS, tile_rows(t), p.C, tid);
+        if (!self_attn) wf_prefetch(raw + raw_kv, p.kv_src, p.wo, (uint32_t)t * WF_ROWS, tile_rows(t), p.C, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // phase A of tile t: rows -> LayerNorm -> bf16 A1 (UMMA layout)
+    auto produce = [&](int t, uint32_t buf) {
+        const uint32_t m0row = (uint32_t)t * WF_ROWS;
+        const int nrows = tile_rows(t);
+        const float* qs = RAW ? reinterpret_cast<const float*>(smem + L.raw + buf * L.raw_stride) : p.q_src;
+        const float* kvs = RAW ? reinterpret_cast<const float*>(smem + L.raw + buf * L.raw_stride + raw_kv) : p.kv_src;
+        if (p.ln_q_g) wf_produce<LPR, true, RAW>(smem + L.a1q, qs, p.ln_q_g, p.ln_q_b, p.eps, p.wo, m0row, nrows, p.C, tid);
+        else wf_produce<LPR, false, RAW>(smem + L.a1q, qs, nullptr, nullptr, p.eps, p.wo, m0row, nrows, p.C, tid);
         if (!self_attn) {
-            if (p.ln_kv_g) wf_produce<LPR, true>(smem + L.a1kv, p.kv_src, p.ln_kv_g, p.ln_kv_b, p.eps, p.wo, m0row, nrows, p.C, tid);
-            else wf_produce<LPR, false>(smem + L.a1kv, p.kv_src, nullptr, nullptr, p.eps, p.wo, m0row, nrows, p.C, tid);
+            if (p.ln_kv_g) wf_produce<LPR, true, RAW>(smem + L.a1kv, kvs, p.ln_kv_g, p.ln_kv_b, p.eps, p.wo, m0row, nrows, p.C, tid);
+            else wf_produce<LPR, false, RAW>(smem + L.a1kv, kvs, nullptr, nullptr, p.eps, p.wo, m0row, nrows, p.C, tid);
         }
         fence_async_smem();
-        __syncthreads();
-
-        // ---- B: q|k|v projection on tcgen05 -------------------------------------------------------------------------------
-        if (tid == 0) {
-            if (it == 0) mbar_wait(w_full, 0);
-            tc_fence_after_sync();
-            const uint32_t a1q = smem_u32(smem + L.a1q), wq = smem_u32(smem + L.wq);
-            if (self_attn) {
-                const uint32_t lbo_w = (uint32_t)NQKV * 16u, idesc = make_idesc_bf16(128, (uint32_t)NQKV);
-                for (uint32_t ks = 0; ks < (uint32_t)Kpad >> 4; ks++)
-                    umma_bf16(tmem_base, make_smem_desc(a1q + ks * 2u * WF_LBO, WF_LBO, WF_SBO),
-                              make_smem_desc(wq + ks * 2u * lbo_w, lbo_w, WF_SBO), idesc, ks > 0);
-            } else {
-                const uint32_t a1kv = smem_u32(smem + L.a1kv), wkv = smem_u32(smem + L.wkv);
-                const uint32_t lbo_q = (uint32_t)HW * 16u, lbo_kv = 2u * (uint32_t)HW * 16u;
-                const uint32_t idq = make_idesc_bf16(128, (uint32_t)HW), idkv = make_idesc_bf16(128, 2u * (uint32_t)HW);
-                for (uint32_t ks = 0; ks < (uint32_t)Kpad >> 4; ks++)
-                    umma_bf16(tmem_base, make_smem_desc(a1q + ks * 2u * WF_LBO, WF_LBO, WF_SBO),
-                              make_smem_desc(wq + ks * 2u * lbo_q, lbo_q, WF_SBO), idq, ks > 0);
-                for (uint32_t ks = 0; ks < (uint32_t)Kpad >> 4; ks++)
-                    umma_bf16(tmem_base + (uint32_t)HW, make_smem_desc(a1kv + ks * 2u * WF_LBO, WF_LBO, WF_SBO),
-                              make_smem_desc(wkv + ks * 2u * lbo_kv, lbo_kv, WF_SBO), idkv, ks > 0);
-            }
-            umma_commit(d1_full);
+    };
+    // phase B: q|k|v projection of the tile in A1 -> D1 (one thread)
+    auto issue_mma1 = [&]() {
+        const uint32_t a1q = smem_u32(smem + L.a1q), wq = smem_u32(smem + L.wq);
+        if (self_attn) {
+            const uint32_t lbo_w = (uint32_t)NQKV * 16u, idesc = make_idesc_bf16(128, (uint32_t)NQKV);
+            for (uint32_t ks = 0; ks < (uint32_t)Kpad >> 4; ks++)
+                umma_bf16(tmem_base, make_smem_desc(a1q + ks * 2u * WF_LBO, WF_LBO, WF_SBO),
+                          make_smem_desc(wq + ks * 2u * lbo_w, lbo_w, WF_SBO), idesc, ks > 0);
+        } else {
+            const uint32_t a1kv = smem_u32(smem + L.a1kv), wkv = smem_u32(smem + L.wkv);
+            const uint32_t lbo_q = (uint32_t)HW * 16u, lbo_kv = 2u * (uint32_t)HW * 16u;
+            const uint32_t idq = make_idesc_bf16(128, (uint32_t)HW), idkv = make_idesc_bf16(128, 2u * (uint32_t)HW);
+            for (uint32_t ks = 0; ks < (uint32_t)Kpad >> 4; ks++)
+                umma_bf16(tmem_base, make_smem_desc(a1q + ks * 2u * WF_LBO, WF_LBO, WF_SBO),
+                          make_smem_desc(wq + ks * 2u * lbo_q, lbo_q, WF_SBO), idq, ks > 0);
+            for (uint32_t ks = 0; ks < (uint32_t)Kpad >> 4; ks++)
+                umma_bf16(tmem_base + (uint32_t)HW, make_smem_desc(a1kv + ks * 2u * WF_LBO, WF_LBO, WF_SBO),
+                          make_smem_desc(wkv + ks * 2u * lbo_kv, lbo_kv, WF_SBO), idkv, ks > 0);
         }
-        __syncwarp();   // warp 0 reconverges before it spins: lanes 1..31 do not compete with the issuing lane
-        mbar_wait_relaxed(d1_full, it & 1u);
-        __syncwarp();
-        tc_fence_after_sync();
-
-        // ---- C: D1 -> + bias -> fp16 q|k|v rows in shared memory ------------------------------------------------------------
-        {
-            uint8_t* qrow = smem + L.qkv + (uint32_t)row * PITCH;
+        umma_commit(d1_full);
+    };
+    // phase C: D1 -> + bias -> fp16 q|k|v rows in shared memory
+    auto qkv_rows = [&](int nrows) {
+        uint8_t* qrow = smem + L.qkv + (uint32_t)row * PITCH;
 #pragma unroll
-            for (int c16 = 0; c16 < NQKV / 2; c16 += 16) {
-                const int col = eg * (NQKV / 2) + c16;
-                float v[16];
-                tmem_ld16(tlane + (uint32_t)col, v);
-                if (row < nrows) {
+        for (int c16 = 0; c16 < NQKV / 2; c16 += 16) {
+            const int col = eg * (NQKV / 2) + c16;
+            float v[16];
+            tmem_ld16(tlane + (uint32_t)col, v);
+            if (row < nrows) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i);
-                        v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(qrow + col * 2);
-                    dst[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
-                    dst[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i);
+                    v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
                 }
+                uint4* dst = reinterpret_cast<uint4*>(qrow + col * 2);
+                dst[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+                dst[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
             }
         }
         tc_fence_before_sync();
-        __syncthreads();
+    };
 
-        // ---- D: attention core, window by window ------------------------------------------------------------------------------
+    // ---- software pipeline over this CTA's tiles t_0, t_1, ... (t_i = blockIdx.x + i * gridDim.x) ------------------------
+    //   iteration i:   [prefetch rows of t_{i+2}]  A(t_{i+1})  D(t_i)  |sync|  issue E(t_i), B(t_{i+1})   F(t_i)  C(t_{i+1})  |sync|
+    // so the gather latency of a tile is spent two attention phases earlier, the q|k|v GEMM of the next tile runs under
+    // the scatter of this one, and a tile costs two block barriers.
+    int t = blockIdx.x;
+    if (t < ntiles) {
+        if (RAW) {
+            prefetch(t, 0u);
+            if (t + (int)gridDim.x < ntiles) prefetch(t + gridDim.x, 1u);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            if (t + (int)gridDim.x >= ntiles) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
+        produce(t, 0u);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(w_full, 0);
+            tc_fence_after_sync();
+            issue_mma1();
+        }
+        __syncwarp();
+        mbar_wait_relaxed(d1_full, 0u);
+        __syncwarp();
+        tc_fence_after_sync();
+        qkv_rows(tile_rows(t));
+    }
+    uint32_t it = 0;
 #pragma unroll 1
-        for (int w = 0; w < nw; w++) {
-            uint32_t m0 = 0, m1 = 0;
-            if (g.shift) {   // boundary windows of the shifted frame are the only ones whose tokens span several regions
-                const uint32_t win = (uint32_t)(win0 + w);
-                const uint32_t wi = win - fdiv(win, p.wo.dnW) * (uint32_t)(g.nWh * g.nWw);
-                const uint32_t wh = fdiv(wi, p.wo.dnWw), ww = wi - wh * (uint32_t)g.nWw;
-                if (wh == (uint32_t)g.nWh - 1) { m0 |= sm.mh0; m1 |= sm.mh1; }
-                if (ww == (uint32_t)g.nWw - 1) { m0 |= sm.mw0; m1 |= sm.mw1; }
+    for (; t < ntiles; t += gridDim.x, it++) {
+        const int tn = t + gridDim.x;
+        const bool has_next = tn < ntiles;
+        const int nw = min(WF_WIN, p.nwin - t * WF_WIN);
+        const int nrows = nw * WF_T;
+        const uint32_t m0row = (uint32_t)t * WF_ROWS;
+        if (RAW) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's share of the rows of t_{i+1} has landed
+        __syncthreads();   // q|k|v rows of t_i and the staged rows of t_{i+1} are visible to every warp
+        if (RAW && tn + (int)gridDim.x < ntiles) prefetch(tn + gridDim.x, it & 1u);   // buffer of t_i: consumed an iteration ago
+        if (has_next) produce(tn, (it + 1u) & 1u);
+
+        // ---- D: attention core of t_i, window by window ---------------------------------------------------------------------
+        if (!(p.debug & 1)) {
+#pragma unroll 1
+            for (int w = 0; w < nw; w++) {
+                uint32_t m0 = 0, m1 = 0;
+                if (g.shift) {   // boundary windows of the shifted frame are the only ones whose tokens span several regions
+                    const uint32_t win = (uint32_t)(t * WF_WIN + w);
+                    const uint32_t wi = win - fdiv(win, p.wo.dnW) * (uint32_t)(g.nWh * g.nWw);
+                    const uint32_t wh = fdiv(wi, p.wo.dnWw), ww = wi - wh * (uint32_t)g.nWw;
+                    if (wh == (uint32_t)g.nWh - 1) { m0 |= sm.mh0; m1 |= sm.mh1; }
+                    if (ww == (uint32_t)g.nWw - 1) { m0 |= sm.mw0; m1 |= sm.mw1; }
+                }
+                const __half* wbase = reinterpret_cast<const __half*>(smem + L.qkv) + w * WF_T * PH;
+                if (DP4) wf_attn_pack4<PH, HW>(wbase, smem + L.a2, w * WF_T, bias, m0, m1, p.d, r0, gq, tq, par);
+                else wf_attn_dp8<PH, HW>(wbase, smem + L.a2, w * WF_T, bias, m0, m1, p.d, r0, gq, tq, par, lane);
             }
-            const __half* wbase = reinterpret_cast<const __half*>(smem + L.qkv) + w * WF_T * PH;
-            if (DP4) wf_attn_pack4<PH, HW>(wbase, smem + L.a2, w * WF_T, bias, m0, m1, p.d, r0, gq, tq, par);
-            else wf_attn_dp8<PH, HW>(wbase, smem + L.a2, w * WF_T, bias, m0, m1, p.d, r0, gq, tq, par, lane);
         }
         fence_async_smem();
-        __syncthreads();
+        __syncthreads();   // A2(t_i) and A1(t_{i+1}) complete; q|k|v rows and staged rows consumed
 
-        // ---- E: output projection on tcgen05 ------------------------------------------------------------------------------------
+        // ---- E(t_i) and B(t_{i+1}) on tcgen05 ------------------------------------------------------------------------------------
         if (tid == 0) {
             tc_fence_after_sync();
             const uint32_t a2 = smem_u32(smem + L.a2), wo = smem_u32(smem + L.wo);
@@ -455,38 +512,52 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_wa_fused(WaFused p) {
                 umma_bf16(tmem_base + D2_COL, make_smem_desc(a2 + ks * 2u * WF_LBO, WF_LBO, WF_SBO),
                           make_smem_desc(wo + ks * 2u * lbo_o, lbo_o, WF_SBO), idesc, ks > 0);
             umma_commit(d2_full);
+            if (has_next) issue_mma1();
         }
-        // the destination row of this thread while the MMA runs: window reverse + un-shift as index math
+        // ---- F: D2 + b_o + residual -> fp32 rows, scattered back (window reverse + un-shift as index math) -------------------------
+        // destination row and residual (an L2 hit: the gather read it moments ago) are fetched while the MMA runs
         const long long mo = row < nrows ? win_order_token(p.wo, m0row + (uint32_t)row) : 0;
+        float4 res[2][4];
+#pragma unroll
+        for (int gi = 0; gi < 2; gi++) {
+            const int c16 = eg * 16 + gi * 32;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                res[gi][i] = (p.residual && row < nrows && c16 + i * 4 + 4 <= p.C)
+                                 ? *reinterpret_cast<const float4*>(p.residual + mo * p.C + c16 + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncwarp();
         mbar_wait_relaxed(d2_full, it & 1u);
         __syncwarp();
         tc_fence_after_sync();
-
-        // ---- F: D2 + b_o + residual -> fp32 rows, scattered back ------------------------------------------------------------------
-        for (int c16 = eg * 16; c16 < N2; c16 += 32) {
-            float v[16];
-            tmem_ld16(tlane + D2_COL + (uint32_t)c16, v);
-            if (row < nrows) {
-                float* o = p.out + mo * p.C + c16;
-                const float* rs = p.residual ? p.residual + mo * p.C + c16 : nullptr;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    if (c16 + i + 4 <= p.C) {
-                        const float4 bb = *reinterpret_cast<const float4*>(sbias + NQKV + c16 + i);
-                        float4 tv = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
-                        if (rs) {
-                            const float4 rr = *reinterpret_cast<const float4*>(rs + i);
-                            tv.x += rr.x; tv.y += rr.y; tv.z += rr.z; tv.w += rr.w;
+        for (int gi = 0; gi < 2; gi++) {
+            const int c16 = eg * 16 + gi * 32;
+            if (c16 < N2) {   // uniform per warp
+                float v[16];
+                tmem_ld16(tlane + D2_COL + (uint32_t)c16, v);
+                if (row < nrows) {
+                    float* o = p.out + mo * p.C + c16;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (c16 + i * 4 + 4 <= p.C) {
+                            const float4 bb = *reinterpret_cast<const float4*>(sbias + NQKV + c16 + i * 4);
+                            const float4 rr = res[gi][i];
+                            *reinterpret_cast<float4*>(o + i * 4) = make_float4(v[i * 4] + bb.x + rr.x, v[i * 4 + 1] + bb.y + rr.y,
+                                                                              v[i * 4 + 2] + bb.z + rr.z, v[i * 4 + 3] + bb.w + rr.w);
                         }
-                        *reinterpret_cast<float4*>(o + i) = tv;
                     }
                 }
             }
         }
         tc_fence_before_sync();
-        // no barrier here: the next tile's phase A only writes A1 (its MMA has completed), and the barrier that ends it
-        // orders every thread's D2 reads before the next MMA pair is issued
+        // ---- C(t_{i+1}): its q|k|v rows replace those of t_i (consumed before the barrier above) ----------------------------------
+        if (has_next) {
+            mbar_wait_relaxed(d1_full, (it + 1u) & 1u);
+            __syncwarp();
+            tc_fence_after_sync();
+            qkv_rows(tile_rows(tn));
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -504,13 +575,13 @@ bool wa_fused_supported(const WinGeom& g, int C, int nh, int d) {
     if (!(d <= 3 || (dp == 8 && d < 8))) return false;   // the softmax row sums ride on a spare (ones) column of every v head
     if (C % 4 != 0 || (int)pad16((uint32_t)C) > 64) return false;
     const int Kpad = (int)pad16((uint32_t)C), N2 = Kpad;
-    const size_t need = d <= 3 ? wf_layout<true>(Kpad, N2, false).total : wf_layout<false>(Kpad, N2, false).total;
+    const size_t need = d <= 3 ? wf_layout<true>(Kpad, N2, false, C).total : wf_layout<false>(Kpad, N2, false, C).total;
     return need <= WF_SMEM_LIMIT;
 }
 
 template <bool DP4>
 static int launch_wa_fused_t(const WaFused& a, cudaStream_t st) {
-    const WfSmem L = wf_layout<DP4>(a.Kpad, a.N2, a.self_attn != 0);
+    const WfSmem L = wf_layout<DP4>(a.Kpad, a.N2, a.self_attn != 0, a.C);
     static DeviceOnce configured;
     if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_wa_fused<DP4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_LIMIT);
@@ -543,6 +614,8 @@ int launch_wa_fused(const sf_window_attn_params* p, const WinGeom& g, bool self_
     a.Wq = Wq; a.bq = bq; a.Wkv = Wkv; a.bkv = bkv; a.Wo = Wo; a.bo = bo; a.table = p->bias_table;
     a.wo = make_winorder(g);
     a.nwin = (int)nwin; a.C = p->C; a.d = p->head_dim; a.Kpad = (int)pad16((uint32_t)p->C); a.N2 = a.Kpad; a.self_attn = self_attn ? 1 : 0;
+    static const int dbg = [] { const char* e = getenv("SWINFUSE_WF_DEBUG"); return e ? atoi(e) : 0; }();
+    a.debug = dbg;
     return p->head_dim <= 3 ? launch_wa_fused_t<true>(a, st) : launch_wa_fused_t<false>(a, st);
 }
 

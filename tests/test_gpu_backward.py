@@ -301,3 +301,40 @@ def test_direct_parameter_gradient_accumulation_equals_autograd_accumulation():
             continue   # analytically zero gradients: round-off of the atomics' order on both sides
         e = float((res[True][n] - ref).abs().max()) / max(float(ref.abs().max()), 0.05 * gscale)
         assert e <= 1e-4, (n, e)
+
+
+@pytest.mark.parametrize("b,h,w,c,hid", [(2, 9, 7, 24, 96), (1, 16, 16, 24, 4), (3, 23, 11, 48, 192), (2, 19, 13, 96, 384),
+                                         (1, 17, 15, 192, 768), (2, 14, 14, 384, 1536), (4, 70, 70, 48, 192)])
+def test_tcgen05_mlp_backward_vs_torch_autograd(b, h, w, c, hid):
+    """SF_PREC_BF16 MLP backward: forward recompute and dX through k_tc_gemm2 (transposed weight images), dW / db through
+    k_tc_wgrad (both operands MN-major bf16 tiles, TMEM accumulation over all token tiles) -- against fp32 torch autograd
+    of  x + W2 ELU(W1 LN(x) + b1) + b2  (a003:21-50 + a004:29-38).  Shapes: ragged token counts (tail rows of the last
+    tile), 1..12 m-blocks and 1..6 n-blocks of the weight-gradient GEMM, hidden < 16.  bf16 operands: 2e-2 of each
+    tensor's scale."""
+    sw = dropin()
+    g = torch.Generator().manual_seed(1000 * c + hid + h)
+    x = torch.randn(b, c, h, w, generator=g)
+    w1, b1 = torch.randn(hid, c, 1, 1, generator=g) * c ** -0.5, 0.1 * torch.randn(hid, generator=g)
+    w2, b2 = torch.randn(c, hid, 1, 1, generator=g) * hid ** -0.5, 0.1 * torch.randn(c, generator=g)
+    lg, lb = 1 + 0.2 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    gout = torch.randn(b, c, h, w, generator=g)
+    names = ["x", "lg", "lb", "w1", "b1", "w2", "b2"]
+
+    def leaves():
+        return [t.clone().cuda().requires_grad_(True) for t in (x, lg, lb, w1, b1, w2, b2)]
+
+    ref = leaves()
+    rx, rlg, rlb, rw1, rb1, rw2, rb2 = ref
+    n = torch.nn.functional.layer_norm(rx.permute(0, 2, 3, 1), (c,), rlg, rlb, 1e-5).permute(0, 3, 1, 2)
+    hdn = torch.nn.functional.elu(torch.nn.functional.conv2d(n, rw1, rb1))
+    out_ref = rx + torch.nn.functional.conv2d(hdn, rw2, rb2)
+    (out_ref * gout.cuda()).sum().backward()
+
+    got = leaves()
+    gx, glg, glb, gw1, gb1, gw2, gb2 = got
+    out = sw.ops.mlp(gx, w1=gw1, b1=gb1, w2=gw2, b2=gb2, ln=(glg, glb), residual=gx, precision="bf16")
+    assert rel_err(out, out_ref) <= 2e-2
+    (out * gout.cuda()).sum().backward()
+    for name, a, r in zip(names, got, ref):
+        err = float((a.grad - r.grad).abs().max() / r.grad.abs().max())
+        assert err <= 2e-2, (name, err)
