@@ -33,6 +33,11 @@ int patch_pack_bf16(const sf_patch_params* p, void* packed, size_t bytes, cudaSt
 struct PackSrc { const float* w[3]; const float* b[3]; };
 int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
                 int k_chunks, cudaStream_t st, int transposed = 0);
+// Up to MAX images in one launch: image i is that of W_i ([N][K] row-major, or -- transposed -- stored [K][N]) with its
+// zero-padded bias; plan fields as launch_pack's (NR = n-chunk rows, KR = k-slab width).
+struct PackJob { const float* w; const float* b; int N, K, transposed; bf16* out; float* bias_out; int NR, KR, n_chunks, k_chunks; };
+struct PackJobs { static constexpr int MAX = 8; int n; PackJob job[MAX]; };
+int launch_pack_jobs(const PackJobs& jobs, cudaStream_t st);
 // Same images, but the N axis is a concatenation of sources with their own layout: source s has
 // rows[s] packed rows; head_padded[s] != 0 means packed row n' = h*dp + dd maps to source row h*d + dd
 // (zero when dd >= d); weights and bias of source s are multiplied by scale[s].

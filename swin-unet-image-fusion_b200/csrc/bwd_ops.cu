@@ -683,14 +683,12 @@ static bool bwd_tc_enabled() {
 static inline size_t tiled_bytes(long long M, int cols) { return tiled_elems(M, cols) * sizeof(bf16); }
 
 // image of W (rows = output features, as stored) with its bias: the forward GEMM  y = x W^T + b
-static int pack_fwd(const float* W, const float* b, int N, int K, const PackedGemm& g, char* base, cudaStream_t st) {
-    PackSrc s{{W, nullptr, nullptr}, {b, nullptr, nullptr}};
-    return launch_pack(s, 1, N, K, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs, st);
+static void pack_fwd(PackJobs& jobs, const float* W, const float* b, int N, int K, const PackedGemm& g, char* base) {
+    jobs.job[jobs.n++] = PackJob{W, b, N, K, 0, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
 }
 // image of W^T for W stored [R][Cc]: the data-gradient GEMM  dX[M x Cc] = dY[M x R] W
-static int pack_tr(const float* W, int R, int Cc, const PackedGemm& g, char* base, cudaStream_t st) {
-    PackSrc s{{W, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-    return launch_pack(s, 1, Cc, R, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs, st, 1);
+static void pack_tr(PackJobs& jobs, const float* W, int R, int Cc, const PackedGemm& g, char* base) {
+    jobs.job[jobs.n++] = PackJob{W, nullptr, Cc, R, 1, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
 }
 // out = A_tiled[M x K] * image^T:  fp32 rows (optionally accumulated into `out_f32`) or bf16 tiled (optionally x ELU'(aux))
 static int tc_gemm_tiled(const bf16* A, long long M, int K, int N, const PackedGemm& g, const char* pk, bool with_bias, bool elu,
@@ -745,9 +743,11 @@ static int mlp_bwd_tc(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes
     bf16* g_t = reinterpret_cast<bf16*>(base + m.off_g);
     bf16* gh_t = reinterpret_cast<bf16*>(base + m.off_gh);
     float* gn = reinterpret_cast<float*>(base + m.off_gn);
-    SF_TRY(pack_fwd(p->w1, p->b1, H, C, m.w1, pk, st));
-    SF_TRY(pack_tr(p->w2, C, H, m.w2t, pk, st));
-    SF_TRY(pack_tr(p->w1, H, C, m.w1t, pk, st));
+    PackJobs jobs{};
+    pack_fwd(jobs, p->w1, p->b1, H, C, m.w1, pk);
+    pack_tr(jobs, p->w2, C, H, m.w2t, pk);
+    pack_tr(jobs, p->w1, H, C, m.w1t, pk);
+    SF_TRY(launch_pack_jobs(jobs, st));
     // recompute: n = LN(x) (or x), a = ELU(n W1^T + b1), both kept as bf16 tiles
     SF_TRY(launch_ln_to_tiled(p->in, p->ln_gamma, p->ln_beta, n_t, M, C, p->ln_eps, st));
     SF_TRY(tc_gemm_tiled(n_t, M, C, H, m.w1, pk, true, true, nullptr, false, h_t, nullptr, "bwd_tc_recompute_mlp1", st));
@@ -760,6 +760,136 @@ static int mlp_bwd_tc(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes
     SF_TRY(tc_gemm_tiled(gh_t, M, H, C, m.w1t, pk, false, false, gdst, false, nullptr, nullptr, "bwd_tc_dx_mlp1", st));
     if (p->ln_gamma) SF_TRY(launch_ln_bwd(p->in, p->ln_gamma, p->ln_beta, gn, bp->g_in, bp->g_ln_gamma, bp->g_ln_beta, M, C, p->ln_eps, false, bp->add_to_g_in, st));
     else if (bp->add_to_g_in) SF_TRY(sf_add(bp->g_in, bp->add_to_g_in, bp->g_in, M * C, (void*)st));
+    return SF_OK;
+}
+
+
+// ---- window attention ------------------------------------------------------------------------------------------------------
+static inline void wa_bwd_ln_plan(const sf_window_attn_params* p, bool* need_q, bool* need_kv, bool* share);
+struct WaBwdPlan {
+    PackedGemm wq, wk, wv, wot, wqt, wkt, wvt;
+    bool share;
+    size_t off_pk, off_nq, off_nkv, off_g, off_o, off_dq, off_dk, off_dv, off_f32, off_gn, total;
+};
+static WaBwdPlan wa_bwd_tc_plan(const sf_window_attn_params* p) {
+    WaBwdPlan w{};
+    const long long M = (long long)p->B * p->Hp * p->Wp;
+    const int C = p->C, inner = p->num_heads * p->head_dim;
+    bool nq, nkv;
+    wa_bwd_ln_plan(p, &nq, &nkv, &w.share);
+    Carver pc;
+    w.wq = plan_packed(pc, inner, C); w.wk = plan_packed(pc, inner, C); w.wv = plan_packed(pc, inner, C);   // q, k, v = n W^T + b
+    w.wot = plan_packed(pc, inner, C);                                                                       // g_O = gout W_o
+    w.wqt = plan_packed(pc, C, inner); w.wkt = plan_packed(pc, C, inner); w.wvt = plan_packed(pc, C, inner); // g_n = dQ W_q + ...
+    Carver c;
+    w.off_pk = c.take(pc.off);
+    w.off_nq = c.take(tiled_bytes(M, C));
+    w.off_nkv = c.take(w.share ? 0 : tiled_bytes(M, C));
+    w.off_g = c.take(tiled_bytes(M, C));
+    w.off_o = c.take(tiled_bytes(M, inner));
+    w.off_dq = c.take(tiled_bytes(M, inner));
+    w.off_dk = c.take(tiled_bytes(M, inner));
+    w.off_dv = c.take(tiled_bytes(M, inner));
+    w.off_f32 = c.take(8 * align_up((size_t)M * inner * sizeof(float)));
+    w.off_gn = c.take(2 * align_up((size_t)M * C * sizeof(float)));
+    w.total = c.off;
+    return w;
+}
+static bool wa_bwd_tc_ok(const sf_window_attn_params* p) {
+    const int inner = p->num_heads * p->head_dim;
+    return bwd_tc_enabled() && p->C % 4 == 0 && (int)tc::pad16((uint32_t)p->C) <= TC_MAX_KPAD && inner % 4 == 0 &&
+           (int)tc::pad16((uint32_t)inner) <= TC_MAX_KPAD && aligned16(p->q_src) && aligned16(p->kv_src) &&
+           (long long)p->B * p->Hp * p->Wp < 2147483647LL;
+}
+static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
+                                const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st, bool mma,
+                                float* O_out);
+static int window_attn_bwd_tc(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
+    const sf_window_attn_params* p = &bp->fwd;
+    const long long M = (long long)p->B * p->Hp * p->Wp;
+    const int C = p->C, inner = p->num_heads * p->head_dim;
+    const WaBwdPlan w = wa_bwd_tc_plan(p);
+    if (ws_bytes < w.total || !ws_ptr) { set_error("sf_window_attn_bwd: workspace too small (%zu B given, %zu needed)", ws_bytes, w.total); return SF_ERR_WORKSPACE; }
+    char* base = reinterpret_cast<char*>(ws_ptr);
+    char* pk = base + w.off_pk;
+    bf16* nq_t = reinterpret_cast<bf16*>(base + w.off_nq);
+    bf16* nkv_t = w.share ? nq_t : reinterpret_cast<bf16*>(base + w.off_nkv);
+    bf16* g_t = reinterpret_cast<bf16*>(base + w.off_g);
+    bf16* o_t = reinterpret_cast<bf16*>(base + w.off_o);
+    bf16* dq_t = reinterpret_cast<bf16*>(base + w.off_dq);
+    bf16* dk_t = reinterpret_cast<bf16*>(base + w.off_dk);
+    bf16* dv_t = reinterpret_cast<bf16*>(base + w.off_dv);
+    const size_t fs = align_up((size_t)M * inner * sizeof(float)), cs = align_up((size_t)M * C * sizeof(float));
+    float* Q = reinterpret_cast<float*>(base + w.off_f32);
+    float* K = reinterpret_cast<float*>(base + w.off_f32 + fs);
+    float* V = reinterpret_cast<float*>(base + w.off_f32 + 2 * fs);
+    float* O = reinterpret_cast<float*>(base + w.off_f32 + 3 * fs);
+    float* gO = reinterpret_cast<float*>(base + w.off_f32 + 4 * fs);
+    float* dQ = reinterpret_cast<float*>(base + w.off_f32 + 5 * fs);
+    float* dK = reinterpret_cast<float*>(base + w.off_f32 + 6 * fs);
+    float* dV = reinterpret_cast<float*>(base + w.off_f32 + 7 * fs);
+    float* gnq = reinterpret_cast<float*>(base + w.off_gn);
+    float* gnkv = reinterpret_cast<float*>(base + w.off_gn + cs);
+    bool need_q, need_kv, share;
+    wa_bwd_ln_plan(p, &need_q, &need_kv, &share);
+    const bool self_src = p->kv_src == p->q_src;
+    SF_CHECK_ARG(share || bp->g_kv_src || self_src, "sf_window_attn_bwd: g_kv_src is required for cross attention");
+    PackJobs jobs{};
+    pack_fwd(jobs, p->wq, p->bq, inner, C, w.wq, pk);
+    pack_fwd(jobs, p->wk, p->bk, inner, C, w.wk, pk);
+    pack_fwd(jobs, p->wv, p->bv, inner, C, w.wv, pk);
+    pack_tr(jobs, p->wo, C, inner, w.wot, pk);
+    pack_tr(jobs, p->wq, inner, C, w.wqt, pk);
+    pack_tr(jobs, p->wk, inner, C, w.wkt, pk);
+    pack_tr(jobs, p->wv, inner, C, w.wvt, pk);
+    SF_TRY(launch_pack_jobs(jobs, st));
+    // ---- recompute the forward: normalised operands (bf16 tiles), q / k / v (fp32 rows for the attention-core adjoint) --------
+    SF_TRY(launch_ln_to_tiled(p->q_src, p->ln_q_gamma, p->ln_q_beta, nq_t, M, C, p->ln_eps, st));
+    if (!share) SF_TRY(launch_ln_to_tiled(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, nkv_t, M, C, p->ln_eps, st));
+    SF_TRY(tc_gemm_tiled(nq_t, M, C, inner, w.wq, pk, true, false, Q, false, nullptr, nullptr, "bwd_tc_recompute_qkv", st));
+    SF_TRY(tc_gemm_tiled(nkv_t, M, C, inner, w.wk, pk, true, false, K, false, nullptr, nullptr, "bwd_tc_recompute_qkv", st));
+    SF_TRY(tc_gemm_tiled(nkv_t, M, C, inner, w.wv, pk, true, false, V, false, nullptr, nullptr, "bwd_tc_recompute_qkv", st));
+    WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
+    const bool fused_o = attn_core_bwd_mma_supported(geom, p->head_dim, p->num_heads);
+    if (!fused_o) SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
+    // ---- output projection: gradient w.r.t. O ---------------------------------------------------------------------------------
+    SF_TRY(launch_ln_to_tiled(bp->gout, nullptr, nullptr, g_t, M, C, 0.f, st));
+    SF_TRY(tc_gemm_tiled(g_t, M, C, inner, w.wot, pk, false, false, gO, false, nullptr, nullptr, "bwd_tc_dx_proj", st));
+    // ---- attention core -------------------------------------------------------------------------------------------------------
+    SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, true,
+                                fused_o ? O : nullptr));
+    SF_TRY(launch_ln_to_tiled(O, nullptr, nullptr, o_t, M, inner, 0.f, st));
+    SF_TRY(launch_ln_to_tiled(dQ, nullptr, nullptr, dq_t, M, inner, 0.f, st));
+    SF_TRY(launch_ln_to_tiled(dK, nullptr, nullptr, dk_t, M, inner, 0.f, st));
+    SF_TRY(launch_ln_to_tiled(dV, nullptr, nullptr, dv_t, M, inner, 0.f, st));
+    // ---- weight gradients -------------------------------------------------------------------------------------------------------
+    SF_TRY(launch_tc_wgrad(g_t, o_t, bp->g_wo, bp->g_bo, M, C, inner, "bwd_tc_wgrad", st));
+    SF_TRY(launch_tc_wgrad(dq_t, nq_t, bp->g_wq, bp->g_bq, M, inner, C, "bwd_tc_wgrad", st));
+    SF_TRY(launch_tc_wgrad(dk_t, nkv_t, bp->g_wk, bp->g_bk, M, inner, C, "bwd_tc_wgrad", st));
+    SF_TRY(launch_tc_wgrad(dv_t, nkv_t, bp->g_wv, bp->g_bv, M, inner, C, "bwd_tc_wgrad", st));
+    // ---- gradients w.r.t. the (normalised) operands ---------------------------------------------------------------------------------
+    float* gq_dst = need_q ? gnq : bp->g_q_src;
+    SF_TRY(tc_gemm_tiled(dq_t, M, inner, C, w.wqt, pk, false, false, gq_dst, false, nullptr, nullptr, "bwd_tc_dx_qkv", st));
+    if (share) {
+        SF_TRY(tc_gemm_tiled(dk_t, M, inner, C, w.wkt, pk, false, false, gq_dst, true, nullptr, nullptr, "bwd_tc_dx_qkv", st));
+        SF_TRY(tc_gemm_tiled(dv_t, M, inner, C, w.wvt, pk, false, false, gq_dst, true, nullptr, nullptr, "bwd_tc_dx_qkv", st));
+    } else {
+        float* gkv_dst = need_kv ? gnkv : (bp->g_kv_src ? bp->g_kv_src : gnkv);
+        SF_TRY(tc_gemm_tiled(dk_t, M, inner, C, w.wkt, pk, false, false, gkv_dst, false, nullptr, nullptr, "bwd_tc_dx_qkv", st));
+        SF_TRY(tc_gemm_tiled(dv_t, M, inner, C, w.wvt, pk, false, false, gkv_dst, true, nullptr, nullptr, "bwd_tc_dx_qkv", st));
+    }
+    // ---- LayerNorm adjoints (as in the exact path) ----------------------------------------------------------------------------------
+    if (need_q) SF_TRY(launch_ln_bwd(p->q_src, p->ln_q_gamma, p->ln_q_beta, gnq, bp->g_q_src, bp->g_ln_q_gamma, bp->g_ln_q_beta, M, C, p->ln_eps, false, bp->add_to_g_q_src, st));
+    else if (bp->add_to_g_q_src) SF_TRY(sf_add(bp->g_q_src, bp->add_to_g_q_src, bp->g_q_src, M * C, (void*)st));
+    if (!share) {
+        float* dst = bp->g_kv_src ? bp->g_kv_src : bp->g_q_src;
+        const bool accum = bp->g_kv_src == nullptr;
+        if (need_kv) {
+            SF_TRY(launch_ln_bwd(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, gnkv, dst, bp->g_ln_kv_gamma, bp->g_ln_kv_beta, M, C, p->ln_eps, false, accum ? dst : nullptr, st));
+        } else if (accum) {
+            SF_TRY(sf_add(bp->g_q_src, gnkv, bp->g_q_src, M * C, (void*)st));
+        }
+    }
     return SF_OK;
 }
 
@@ -776,13 +906,15 @@ static inline void wa_bwd_ln_plan(const sf_window_attn_params* p, bool* need_q, 
 
 size_t window_attn_bwd_ws(const sf_window_attn_bwd_params* bp) {
     const sf_window_attn_params* p = &bp->fwd;
+    if (p->precision == SF_PREC_BF16 && wa_bwd_tc_ok(p)) return wa_bwd_tc_plan(p).total;
     const size_t M = (size_t)p->B * p->Hp * p->Wp, inner = (size_t)p->num_heads * p->head_dim;
     return 8 * align_up(M * inner * sizeof(float)) + 4 * align_up(M * p->C * sizeof(float));
 }
 
 int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
-    const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: TF32 tensor-core GEMMs in the backward pass
+    const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: tensor-core GEMMs in the backward pass
     const sf_window_attn_params* p = &bp->fwd;
+    if (tf && wa_bwd_tc_ok(p)) return window_attn_bwd_tc(bp, ws_ptr, ws_bytes, st);
     const long long M = (long long)p->B * p->Hp * p->Wp;
     const int C = p->C, inner = p->num_heads * p->head_dim;
     Workspace ws(ws_ptr, ws_bytes);

@@ -149,6 +149,50 @@ __global__ void k_pack_w_mapped(PackSrc src, PackMap map, int K, bf16* __restric
     }
 }
 
+// several plain / transposed images in ONE launch (blockIdx.y = job): the backward pass packs up to seven images per operator
+__global__ void k_pack_jobs(PackJobs jobs) {
+    const PackJob& j = jobs.job[blockIdx.y];
+    const long long cpi = (long long)j.NR * j.KR / 8;
+    const long long total = cpi * j.n_chunks * j.k_chunks;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const long long img = c / cpi;
+        const int ci = (int)(c - img * cpi);
+        const int jk = (int)(img % j.k_chunks), jn = (int)(img / j.k_chunks);
+        const int kc = ci / j.NR, r = ci - kc * j.NR;
+        const int n = jn * j.NR + r;
+        uint32_t pk[4] = {0, 0, 0, 0};
+        if (n < j.N) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int k = jk * j.KR + kc * 8 + e;
+                v[e] = k < j.K ? (j.transposed ? j.w[(long long)k * j.N + n] : j.w[(long long)n * j.K + k]) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+        }
+        *reinterpret_cast<uint4*>(j.out + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < j.n_chunks * j.NR; n += gridDim.x * blockDim.x)
+        j.bias_out[n] = (n < j.N && j.b) ? j.b[n] : 0.f;
+}
+
+int launch_pack_jobs(const PackJobs& jobs, cudaStream_t st) {
+    SF_CHECK_ARG(jobs.n >= 1 && jobs.n <= PackJobs::MAX, "pack: bad job count %d", jobs.n);
+    long long most = 0;
+    double bytes = 0;
+    for (int i = 0; i < jobs.n; i++) {
+        const PackJob& j = jobs.job[i];
+        most = std::max(most, (long long)j.NR * j.KR / 8 * j.n_chunks * j.k_chunks);
+        bytes += 6.0 * j.N * j.K;
+    }
+    int bx = (int)std::min<long long>((most + 255) / 256, 64);
+    ProfScope ps("pack_weights_bf16", 0.0, bytes, st);
+    k_pack_jobs<<<dim3((unsigned)std::max(bx, 1), (unsigned)jobs.n), 256, 0, st>>>(jobs);
+    SF_CHECK_LAUNCH("pack_weights_bf16");
+    return SF_OK;
+}
+
 int launch_pack_mapped(const PackSrc& src, const PackMap& map, int K, bf16* out, float* bias_out, int NR, int KR, int n_chunks,
                        int k_chunks, cudaStream_t st) {
     long long total = (long long)NR * KR / 8 * n_chunks * k_chunks;
@@ -447,6 +491,60 @@ __global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restr
     }
 }
 
+// Narrow rows (Kpad <= 64): one thread per row -- a warp-per-row mapping would leave most lanes idle at C = 24 / 48.
+// A warp reads 32 consecutive rows (one contiguous span, completed out of L1 over the NF4 loads) and stores
+// 32 consecutive 16-byte chunks per k-chunk.
+template <int NF4>
+__global__ void __launch_bounds__(256) k_ln_to_tiled_rows(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, bf16* __restrict__ out, long long M, int C, int Kpad,
+                                                          float eps, int gather, WinOrder wo) {
+    const int nf4 = C >> 2, nkc = Kpad >> 3;
+    const long long Mpad = (M + 127) / 128 * 128;
+    for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < Mpad; row += (long long)gridDim.x * blockDim.x) {
+        const bool real = row < M;
+        const long long srow = (gather && real) ? win_order_token(wo, (uint32_t)row) : row;
+        const float4* src = reinterpret_cast<const float4*>(in + srow * C);
+        float4 v[NF4];
+#pragma unroll
+        for (int i = 0; i < NF4; i++) v[i] = (real && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gamma && real) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NF4; i++) { s0 += v[i].x + v[i].y; s1 += v[i].z + v[i].w; }
+            const float invc = 1.f / (float)C;
+            const float mean = (s0 + s1) * invc;
+            float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NF4; i++) {
+                if (i < nf4) {
+                    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                    q0 += dx * dx + dy * dy; q1 += dz * dz + dw * dw;
+                }
+            }
+            const float rstd = rsqrtf((q0 + q1) * invc + eps);
+#pragma unroll
+            for (int i = 0; i < NF4; i++) {
+                if (i < nf4) {
+                    const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + i), bb = __ldg(reinterpret_cast<const float4*>(beta) + i);
+                    v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
+                    v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
+                    v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
+                    v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
+                }
+            }
+        }
+        const long long tile = row >> 7;
+        const int r = (int)(row & 127);
+#pragma unroll
+        for (int c = 0; c < NF4 / 2; c++) {
+            if (c < nkc)
+                *reinterpret_cast<uint4*>(out + ((tile * nkc + c) * 128 + r) * 8) =
+                    make_uint4(pack_bf16x2(v[2 * c].x, v[2 * c].y), pack_bf16x2(v[2 * c].z, v[2 * c].w),
+                               pack_bf16x2(v[2 * c + 1].x, v[2 * c + 1].y), pack_bf16x2(v[2 * c + 1].z, v[2 * c + 1].w));
+        }
+    }
+}
+
 int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st,
                        const WinOrder* wo) {
     const int Kpad = (int)pad16((uint32_t)C);
@@ -456,6 +554,15 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
     if (blocks < 1) blocks = 1;
     ProfScope ps(prof_name(gamma ? "ln_to_tiled_c%d" : "cast_to_tiled_c%d", C), gamma ? 8.0 * (double)M * C : 0.0, 6.0 * (double)M * C, st);
     SF_CHECK_ARG(!wo || M < 2147483647LL, "ln_to_tiled: %lld rows exceed the window-order index range", M);
+    if (Kpad <= 64) {
+        long long rb = (M + 255) / 256;
+        if (rb > (long long)sm_count() * 8) rb = (long long)sm_count() * 8;
+        if (rb < 1) rb = 1;
+        if (Kpad <= 32) k_ln_to_tiled_rows<8><<<(unsigned)rb, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
+        else k_ln_to_tiled_rows<16><<<(unsigned)rb, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
+        SF_CHECK_LAUNCH("ln_to_tiled");
+        return SF_OK;
+    }
     k_ln_to_tiled<<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
     SF_CHECK_LAUNCH("ln_to_tiled");
     return SF_OK;

@@ -36,6 +36,7 @@ struct TcWgrad {
     int splits;                   // token-range splits
     long long tiles, tiles_per_split;
     uint32_t bias_col, ncols;     // TMEM: column of the bias-gradient accumulator, columns allocated
+    int vec4;                     // 16-byte vector reductions into Wg
 };
 
 // MN-major, SWIZZLE_NONE operand: `lbo` = bytes between 8-token groups (K direction), `sbo` = bytes between 8-feature
@@ -43,6 +44,10 @@ struct TcWgrad {
 __device__ __forceinline__ uint64_t wg_desc(uint32_t addr) { return make_smem_desc(addr, 128u, WG_CHUNK); }
 __host__ __device__ constexpr uint32_t wg_idesc(uint32_t M, uint32_t N) {
     return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+}
+// Wg[0..3] += v  (one 16-byte reduction at L2 instead of four)
+__device__ __forceinline__ void wg_red4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void wg_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -150,9 +155,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(TcWgrad p) {
                 tmem_ld16(tl + (uint32_t)c16, v);
                 if (n < p.N) {
                     float* dst = p.Wg + (size_t)n * p.K + k0 + c16;
+                    if (p.vec4) {   // K % 4 == 0 and Wg 16-byte aligned: every group of four columns is one aligned vector
 #pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        if (c16 + i < kcols) atomicAdd(dst + i, v[i]);
+                        for (int i = 0; i < 16; i += 4)
+                            if (c16 + i < kcols) wg_red4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if (c16 + i < kcols) atomicAdd(dst + i, v[i]);
+                    }
                 }
             }
             if (has_bias && nb == 0) {
@@ -183,8 +194,11 @@ int launch_tc_wgrad(const bf16* G, const bf16* A, float* Wg, float* bias_grad, l
     p.n_blocks = (p.a_nkc + p.nbc - 1) / p.nbc;
     p.tiles = (M + 127) / 128;
     const long long blocks = (long long)p.m_blocks * p.n_blocks;
-    long long splits = (2LL * sm_count() + blocks - 1) / blocks;
-    splits = std::max(1LL, std::min(splits, p.tiles));
+    // token-range splits: about one work item per SM, and at least eight token tiles per item so that the item's epilogue
+    // (128 x nbc*8 reductions into Wg) is paid for by its streaming phase
+    long long splits = ((long long)sm_count() + blocks - 1) / blocks;
+    splits = std::max(1LL, std::min(splits, (p.tiles + 7) / 8));
+    p.vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wg) & 15) == 0);
     p.tiles_per_split = (p.tiles + splits - 1) / splits;
     p.splits = (int)((p.tiles + p.tiles_per_split - 1) / p.tiles_per_split);
     const uint32_t stage_bytes = WG_GBYTES + (uint32_t)p.nbc * WG_CHUNK;

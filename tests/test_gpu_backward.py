@@ -185,9 +185,10 @@ def test_small_model_training_step_gradients_match_reference_autograd():
 
 
 def test_bf16_mode_gradients_track_the_fp32_ones():
-    """SF_PREC_BF16 operators run their backward GEMMs on TF32 tensor cores (forward on bf16): the gradients of a
-    whole train-mode model step must stay close to the exact
-    fp32 backward: 1e-2 in relative L2 over all parameters, 1.5e-1 of its own scale for any single tensor."""
+    """SF_PREC_BF16 operators run their forward AND backward GEMMs on tcgen05 with bf16 operands (fp32 accumulation; the
+    attention-core adjoint on fp16 mma.sync): the gradients of a whole train-mode model step must stay close to the exact
+    fp32 backward: 2e-2 in relative L2 over all parameters, 2e-1 of its own scale for any single tensor -- the same
+    bounds tests/test_gpu_train.py holds this path to against the REFERENCE's autograd fixtures."""
     sw = dropin()
     g = golden("model_small.npz")
     cfg = small_cfg()
@@ -220,8 +221,8 @@ def test_bf16_mode_gradients_track_the_fp32_ones():
     print("bf16-mode gradient deviation: rel L2 over all parameters", rel_l2, "worst tensor (max-norm)", worst)
     # the deviation is that of the bf16 forward activations (1e-2 on the fused image) seen through the backward pass;
     # sums with cancellation (the 13x13 bias tables) sit highest
-    assert rel_l2 <= 1e-2, rel_l2
-    assert worst[0] <= 1.5e-1, worst
+    assert rel_l2 <= 2e-2, rel_l2
+    assert worst[0] <= 2e-1, worst
 
 
 @pytest.mark.parametrize("c,nh,d", [(24, 8, 3), (48, 8, 6), (96, 8, 12), (192, 8, 24), (384, 8, 48)])
@@ -229,8 +230,9 @@ def test_bf16_mode_gradients_track_the_fp32_ones():
 @pytest.mark.parametrize("cross", [False, True])
 def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted, cross):
     """SF_PREC_BF16 window attention runs its attention-core adjoint on mma.sync (fp16 operands, per-window power-of-two
-    normalisation of dO) and its GEMM adjoints on TF32; the backward recomputes the forward in fp32 in both modes, so the
-    gradients must agree with the exact fp32 backward to operand-rounding level (1e-2 of each tensor's scale: q, k, v are recomputed on TF32 too and the softmax amplifies their rounding), also for
+    normalisation of dO) and every GEMM of its backward (q / k / v recompute, data gradients, weight gradients) on tcgen05
+    with bf16 operands and fp32 accumulation, so the gradients must agree with the exact fp32 backward to operand-rounding
+    level (2e-2 of each tensor's scale: 8-bit mantissas, and the softmax amplifies the rounding of q and k), also for
     upstream gradients as small as a mean-reduced loss produces (1e-7)."""
     sw = dropin()
     from a001_WindowAttention import WindowAttention
@@ -268,7 +270,7 @@ def test_tensor_core_attention_backward_tracks_the_fp32_kernel(c, nh, d, shifted
     for n, ref in res["fp32"].items():
         floor = 0.05 * gscale if n not in ("gq", "gkv") else 0.0
         e = float((res["bf16"][n] - ref).abs().max()) / max(float(ref.abs().max()), floor)
-        assert e <= 1e-2, (n, e)
+        assert e <= 2e-2, (n, e)
 
 
 def test_direct_parameter_gradient_accumulation_equals_autograd_accumulation():
