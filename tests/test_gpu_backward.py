@@ -214,7 +214,8 @@ def test_bf16_mode_gradients_track_the_fp32_ones():
     for name, ref in grads["fp32"].items():
         d = grads["bf16"][name] - ref
         e = float(d.abs().max()) / max(float(ref.abs().max()), 0.05 * gscale)
-        worst = max(worst, (e, name))
+        if not (name.endswith("k_for_heads.bias") or name == "final_layer.0.bias"):   # analytically zero: round-off on both sides
+            worst = max(worst, (e, name))
         num += float((d.double() ** 2).sum())
         den += float((ref.double() ** 2).sum())
     rel_l2 = (num / den) ** 0.5
