@@ -124,6 +124,89 @@ static void launch_ln_small(const float* in, const float* gamma, const float* be
     }
 }
 
+// Wide rows (64 < C <= 768, C % 4 == 0): LPR lanes per row, NPER float4 per lane held in registers (one pass over the row,
+// 16-byte accesses, 32 / LPR rows per warp) -- the scalar warp-per-row kernel above reads the row three times out of L1.
+template <bool ACT, bool UNMERGE, int LPR, int NPER>
+__global__ void __launch_bounds__(256) k_ln_rows_vec(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float* __restrict__ out, long long M, int C, float eps, UnmergeGeom ug) {
+    const int nf4 = C >> 2;
+    const int lane = threadIdx.x & 31, l = lane & (LPR - 1), sub = lane / LPR;
+    constexpr int RPW = 32 / LPR;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float invc = 1.f / (float)C;
+    for (long long r0 = warp0 * RPW; r0 < M; r0 += nwarps * RPW) {
+        const long long row = r0 + sub;
+        const bool ok = row < M;
+        const float4* src = reinterpret_cast<const float4*>(in + (ok ? row : 0) * C);
+        float4 v[NPER];
+#pragma unroll
+        for (int i = 0; i < NPER; i++) v[i] = (ok && l + i * LPR < nf4) ? src[l + i * LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * invc;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; i++) {
+            if (l + i * LPR < nf4) {
+                const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+                q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * invc + eps);
+        if (!ok) continue;
+        long long obase = row * C;
+        int Wf = 0;
+        if (UNMERGE) {   // row = (b, Y, X) of the coarse map; channel n = q*Cout + ch -> fine pixel (Y*mh+ph, X*mw+pw), channel ch
+            const int X = (int)(row % ug.Wc);
+            const long long p = row / ug.Wc;
+            const int Y = (int)(p % ug.Hc);
+            const long long b = p / ug.Hc;
+            Wf = ug.Wc * ug.mw;
+            obase = ((b * (ug.Hc * ug.mh) + (long long)Y * ug.mh) * Wf + (long long)X * ug.mw) * ug.Cout;
+        }
+#pragma unroll
+        for (int i = 0; i < NPER; i++) {
+            const int q4 = l + i * LPR;
+            if (q4 < nf4) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q4), bb = __ldg(reinterpret_cast<const float4*>(beta) + q4);
+                float4 y = make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                                       (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+                if (ACT) { y.x = elu1(y.x); y.y = elu1(y.y); y.z = elu1(y.z); y.w = elu1(y.w); }
+                if (!UNMERGE) {
+                    *reinterpret_cast<float4*>(out + obase + q4 * 4) = y;
+                } else {   // Cout % 4 == 0: the four channels of a float4 belong to one fine pixel
+                    const int c = q4 * 4, qq = c / ug.Cout, ch = c - qq * ug.Cout;
+                    const int ph = qq / ug.mw, pw = qq - ph * ug.mw;
+                    *reinterpret_cast<float4*>(out + obase + ((long long)ph * Wf + pw) * ug.Cout + ch) = y;
+                }
+            }
+        }
+    }
+}
+
+template <int LPR, int NPER>
+static void launch_ln_vec(const float* in, const float* gamma, const float* beta, float* out, long long M, int C, float eps,
+                          int act, const UnmergeGeom* ug, cudaStream_t st) {
+    constexpr int RPW = 32 / LPR;
+    long long blocks = ((M + RPW - 1) / RPW * 32 + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (blocks < 1) blocks = 1;
+    UnmergeGeom g = ug ? *ug : UnmergeGeom{0, 0, 0, 0, 0};
+    if (ug) {
+        if (act) k_ln_rows_vec<true, true, LPR, NPER><<<(int)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+        else k_ln_rows_vec<false, true, LPR, NPER><<<(int)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+    } else {
+        if (act) k_ln_rows_vec<true, false, LPR, NPER><<<(int)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+        else k_ln_rows_vec<false, false, LPR, NPER><<<(int)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, eps, g);
+    }
+}
+
 int launch_layernorm(const float* in, const float* gamma, const float* beta, float* out, long long M, int C, float eps,
                      int act, const UnmergeGeom* ug, cudaStream_t st) {
     const int threads = 256;
@@ -139,6 +222,15 @@ int launch_layernorm(const float* in, const float* gamma, const float* beta, flo
         else if (C <= 32) launch_ln_small<8>(in, gamma, beta, out, M, C, eps, act, ug, st);
         else launch_ln_small<16>(in, gamma, beta, out, M, C, eps, act, ug, st);
         SF_CHECK_LAUNCH("layernorm_small");
+        return SF_OK;
+    }
+    if (C % 4 == 0 && C <= 768 && al && M > 0 && (!ug || ug->Cout % 4 == 0)) {
+        const int nf4 = C >> 2;
+        if (nf4 <= 24) launch_ln_vec<8, 3>(in, gamma, beta, out, M, C, eps, act, ug, st);
+        else if (nf4 <= 48) launch_ln_vec<16, 3>(in, gamma, beta, out, M, C, eps, act, ug, st);
+        else if (nf4 <= 96) launch_ln_vec<32, 3>(in, gamma, beta, out, M, C, eps, act, ug, st);
+        else launch_ln_vec<32, 6>(in, gamma, beta, out, M, C, eps, act, ug, st);
+        SF_CHECK_LAUNCH("layernorm_vec");
         return SF_OK;
     }
     if (ug) {

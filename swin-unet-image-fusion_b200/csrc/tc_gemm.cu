@@ -431,22 +431,26 @@ __device__ __forceinline__ void produce_a_merge(uint8_t* sA, const TcGemm& p, lo
 // GEMMs consuming it run in the STREAM flavour (A arrives by bulk copy, no producer warps in the
 // critical path and no per-n-group recomputation of the LayerNorm).  One warp per row.
 // =============================================================================================
-__global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
-                              bf16* __restrict__ out, long long M, int C, int Kpad, float eps, int gather, WinOrder wo) {
+template <int LPR>
+__global__ void __launch_bounds__(256) k_ln_to_tiled(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     bf16* __restrict__ out, long long M, int C, int Kpad, float eps, int gather, WinOrder wo) {
+    // LPR lanes per row, three float4 per lane (C <= 12 * LPR), 32 / LPR rows per warp.
     // gamma == nullptr: no LayerNorm, a plain fp32 -> bf16 cast into the tiled layout (backward pass operands).
     // Rows M .. 128*ceil(M/128)-1 of the last tile are written as zeros: the weight-gradient GEMM sums over token rows.
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, l = lane & (LPR - 1), sub = lane / LPR;
+    constexpr int RPW = 32 / LPR;
     const int nf4 = C >> 2, nslots = Kpad >> 2, nkc = Kpad >> 3;
     const long long Mpad = (M + 127) / 128 * 128;
-    long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (; row < Mpad; row += stride) {
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r0 = warp0 * RPW; r0 < Mpad; r0 += nwarps * RPW) {
+        const long long row = r0 + sub;
         float4 v[3];
         const bool real = row < M;
         const long long srow = (gather && real) ? win_order_token(wo, (uint32_t)row) : row;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            int q = lane + 32 * i;
+            int q = l + LPR * i;
             v[i] = (real && q < nf4) ? *reinterpret_cast<const float4*>(in + srow * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float mean = 0.f, rstd = 1.f;
@@ -455,25 +459,26 @@ __global__ void k_ln_to_tiled(const float* __restrict__ in, const float* __restr
 #pragma unroll
             for (int i = 0; i < 3; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             mean = s / (float)C;
             float ss = 0.f;
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                if (lane + 32 * i < nf4) {
+                if (l + LPR * i < nf4) {
                     float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
                     ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
                 }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            for (int o = LPR >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
             rstd = rsqrtf(ss / (float)C + eps);
         }
+        if (row >= Mpad) continue;
         const long long tile = row >> 7;
         const int r = (int)(row & 127);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            int q = lane + 32 * i;
+            int q = l + LPR * i;
             if (q < nslots) {
                 uint2 pk = make_uint2(0u, 0u);
                 if (real && q < nf4) {
@@ -563,7 +568,16 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
         SF_CHECK_LAUNCH("ln_to_tiled");
         return SF_OK;
     }
-    k_ln_to_tiled<<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
+    const WinOrder woa = wo ? *wo : WinOrder{};
+    if (Kpad <= 96) {
+        blocks = std::min<long long>((M / 4 * 32 + 255) / 256 + 1, (long long)sm_count() * 16);
+        k_ln_to_tiled<8><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa);
+    } else if (Kpad <= 192) {
+        blocks = std::min<long long>((M / 2 * 32 + 255) / 256 + 1, (long long)sm_count() * 16);
+        k_ln_to_tiled<16><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa);
+    } else {
+        k_ln_to_tiled<32><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa);
+    }
     SF_CHECK_LAUNCH("ln_to_tiled");
     return SF_OK;
 }
