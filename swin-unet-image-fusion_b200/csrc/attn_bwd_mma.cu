@@ -428,16 +428,19 @@ bool attn_core_bwd_mma_supported(const WinGeom& g, int d, int nh) {
 }
 
 int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
-                             const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st) {
+                             const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st, int ld) {
+    // ld: row stride (elements) shared by all eight tensors -- they may be column blocks of one [tokens x ld] buffer
+    if (ld <= 0) ld = inner;
+    SF_CHECK_ARG((long long)g.B * g.Hp * g.Wp * ld < (1LL << 32), "attention backward (mma): %d-wide rows exceed the 32-bit offset range", ld);
     const long long nitems = (long long)g.B * g.nWh * g.nWw * nh;
     const double mtok = (double)g.B * g.Hp * g.Wp;
     ProfScope ps(prof_name("bwd_attn_core_mma_d%d", d), (O ? 14.0 : 12.0) * g.T * mtok * inner, (O ? 32.0 : 28.0) * mtok * inner, st);
     switch (d) {
-        case 3: return launch_one<3>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
-        case 6: return launch_one<6>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
-        case 12: return launch_one<12>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
-        case 24: return launch_one<24>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
-        case 48: return launch_one<48>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, nitems, st);
+        case 3: return launch_one<3>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
+        case 6: return launch_one<6>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
+        case 12: return launch_one<12>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
+        case 24: return launch_one<24>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
+        case 48: return launch_one<48>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
     }
     set_error("attention backward (mma): head_dim %d is not built", d);
     return SF_ERR_INVALID;

@@ -35,7 +35,9 @@ int launch_pack(const PackSrc& src, int nsrc, int Neach, int K, bf16* out, float
                 int k_chunks, cudaStream_t st, int transposed = 0);
 // Up to MAX images in one launch: image i is that of W_i ([N][K] row-major, or -- transposed -- stored [K][N]) with its
 // zero-padded bias; plan fields as launch_pack's (NR = n-chunk rows, KR = k-slab width).
-struct PackJob { const float* w; const float* b; int N, K, transposed; bf16* out; float* bias_out; int NR, KR, n_chunks, k_chunks; };
+// Up to three sources are stacked: along N (plain: rows [s*each, (s+1)*each) come from w[s], b[s]) or along K (transposed:
+// k in [s*each, (s+1)*each) comes from w[s], each stored [each][N]).
+struct PackJob { const float* w[3]; const float* b[3]; int each; int N, K, transposed; bf16* out; float* bias_out; int NR, KR, n_chunks, k_chunks; };
 struct PackJobs { static constexpr int MAX = 8; int n; PackJob job[MAX]; };
 int launch_pack_jobs(const PackJobs& jobs, cudaStream_t st);
 // Same images, but the N axis is a concatenation of sources with their own layout: source s has
@@ -78,6 +80,7 @@ struct TcGemm {
     int win_order;            // GEMM rows are in window order: fp32 A producers gather source rows, OUT_F32 scatters rows
     WinOrder wo;
     // ---- tc_gemm_plan fills ----
+    int a_tile_nkc, a_kc0;    // AM_TILED, optional: A is the chunk range [a_kc0, ..) of a tiled tensor with a_tile_nkc chunks per tile
     int Kpad, KS, n_slabs, a_nkc, NA, NS, n_groups, chunks_per_group;
 };
 void tc_gemm_pick_nchunk(int Ntot, int* NCH, int* n_chunks);
@@ -86,8 +89,10 @@ int tc_gemm_plan(TcGemm* p);          // needs K, a_mode, NCH, n_chunks, M
 int launch_tc_gemm(const TcGemm& p, const char* name, cudaStream_t st);
 // fp32 rows -> LayerNorm -> bf16 UMMA-tiled (pre-pass for wide rows, see tc_gemm.cu)
 // `wo` != null: output row m is the token win_order_token(*wo, m) of `in` (window order)
+// ld_in: row stride of `in` (0 = C); out_nkc / out_kc0: the C columns are written as the chunk range [out_kc0, ..) of a wider
+// tiled tensor with out_nkc chunks per tile (0 = a tensor of its own)
 int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st,
-                       const WinOrder* wo = nullptr);
+                       const WinOrder* wo = nullptr, long long ld_in = 0, int out_nkc = 0, int out_kc0 = 0);
 static constexpr int TC_LN_PREPASS_MIN_C = 96;   // rows at least this wide are normalised by the pre-pass
 
 // ---- workspace carving and packed-weight plans shared by the operator implementations (bf16_path.cu, tc_bwd.cu) ----
@@ -158,5 +163,13 @@ int launch_wa_fused(const sf_window_attn_params* p, const WinGeom& g, bool self_
 // ---- backward pass on tcgen05 (tc_wgrad.cu, tc_bwd.cu) -----------------------------------------------------------------
 // Wg[N][K] += G^T A,  bias_grad[N] += column sums of G;  G: [M x N], A: [M x K], both bf16 UMMA-tiled with zero tail rows
 int launch_tc_wgrad(const bf16* G, const bf16* A, float* Wg, float* bias_grad, long long M, int N, int K, const char* name, cudaStream_t st);
+// General form: the N rows of the product are `nout` stacked weight matrices (N / nout rows each, e.g. [dWq; dWk; dWv]) written
+// to separate tensors; G / A may be chunk ranges [kc0, ..) of wider tiled tensors (tile_nkc chunks per tile; 0 = own tensor).
+struct TcWgradArgs {
+    const bf16* G; const bf16* A; long long M; int N, K;
+    int nout; float* Wg[3]; float* bias_grad[3];
+    int g_tile_nkc, g_kc0, a_tile_nkc, a_kc0;
+};
+int launch_tc_wgrad_ex(const TcWgradArgs& a, const char* name, cudaStream_t st);
 
 }  // namespace sf

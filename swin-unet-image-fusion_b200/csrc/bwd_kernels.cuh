@@ -15,7 +15,7 @@ int head_bwd(const sf_head_bwd_params* p, void* ws, size_t ws_bytes, cudaStream_
 bool attn_core_bwd_mma_supported(const WinGeom& g, int d, int nh);
 // O (optional): also writes the forward output P V, so that the caller need not recompute the attention core
 int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
-                             const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st);
+                             const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st, int ld = 0);
 // gemm_tf32.cu: TF32 tensor-core GEMMs for the backward pass of SF_PREC_BF16 operators
 struct GemmBatch;
 int gemm_tf32_nn(const float* A, const float* B, const float* aux, float* C, long long M, int N, int K, bool accum, cudaStream_t st);

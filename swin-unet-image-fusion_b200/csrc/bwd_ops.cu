@@ -684,11 +684,23 @@ static inline size_t tiled_bytes(long long M, int cols) { return tiled_elems(M, 
 
 // image of W (rows = output features, as stored) with its bias: the forward GEMM  y = x W^T + b
 static void pack_fwd(PackJobs& jobs, const float* W, const float* b, int N, int K, const PackedGemm& g, char* base) {
-    jobs.job[jobs.n++] = PackJob{W, b, N, K, 0, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
+    jobs.job[jobs.n++] = PackJob{{W, nullptr, nullptr}, {b, nullptr, nullptr}, N, N, K, 0, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
+}
+// stacked forward image [W0; W1; (W2)] (each [Neach][K]) with the stacked biases
+static void pack_fwd_stack(PackJobs& jobs, int nsrc, const float* const* W, const float* const* b, int Neach, int K, const PackedGemm& g, char* base) {
+    PackJob j{{W[0], nsrc > 1 ? W[1] : nullptr, nsrc > 2 ? W[2] : nullptr}, {b[0], nsrc > 1 ? b[1] : nullptr, nsrc > 2 ? b[2] : nullptr},
+              Neach, nsrc * Neach, K, 0, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
+    jobs.job[jobs.n++] = j;
+}
+// image of [W0; W1; (W2)]^T (each W stored [R][Cc]): dX[M x Cc] = [dY0 | dY1 | dY2][M x nsrc*R] [W0; W1; W2]
+static void pack_tr_stack(PackJobs& jobs, int nsrc, const float* const* W, int R, int Cc, const PackedGemm& g, char* base) {
+    PackJob j{{W[0], nsrc > 1 ? W[1] : nullptr, nsrc > 2 ? W[2] : nullptr}, {nullptr, nullptr, nullptr},
+              R, Cc, nsrc * R, 1, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
+    jobs.job[jobs.n++] = j;
 }
 // image of W^T for W stored [R][Cc]: the data-gradient GEMM  dX[M x Cc] = dY[M x R] W
 static void pack_tr(PackJobs& jobs, const float* W, int R, int Cc, const PackedGemm& g, char* base) {
-    jobs.job[jobs.n++] = PackJob{W, nullptr, Cc, R, 1, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
+    jobs.job[jobs.n++] = PackJob{{W, nullptr, nullptr}, {nullptr, nullptr, nullptr}, R, Cc, R, 1, (bf16*)(base + g.off_w), (float*)(base + g.off_b), g.nch, g.ks, g.nc, g.nslabs};
 }
 // out = A_tiled[M x K] * image^T:  fp32 rows (optionally accumulated into `out_f32`) or bf16 tiled (optionally x ELU'(aux))
 static int tc_gemm_tiled(const bf16* A, long long M, int K, int N, const PackedGemm& g, const char* pk, bool with_bias, bool elu,
@@ -765,11 +777,15 @@ static int mlp_bwd_tc(const sf_mlp_bwd_params* bp, void* ws_ptr, size_t ws_bytes
 
 
 // ---- window attention ------------------------------------------------------------------------------------------------------
+// The eight fp32 tensors the attention-core adjoint works on are column blocks of ONE [tokens x 8*inner] buffer
+// [Q | K | V | gO | O | dQ | dK | dV], and dQ | dK | dV are cast into ONE bf16 tiled tensor, so that the projections
+// run as stacked GEMMs: q|k|v recompute in one launch (self) or two (cross: q from one source, k|v from the other), the
+// data gradient as one K-concatenated GEMM per source, the three weight gradients as one stacked k_tc_wgrad per source.
 static inline void wa_bwd_ln_plan(const sf_window_attn_params* p, bool* need_q, bool* need_kv, bool* share);
 struct WaBwdPlan {
-    PackedGemm wq, wk, wv, wot, wqt, wkt, wvt;
+    PackedGemm wqkv, wq, wkv, wot, wqkvt, wqt, wkvt;
     bool share;
-    size_t off_pk, off_nq, off_nkv, off_g, off_o, off_dq, off_dk, off_dv, off_f32, off_gn, total;
+    size_t off_pk, off_nq, off_nkv, off_g, off_o, off_dqkv, off_f32, off_gn, total;
 };
 static WaBwdPlan wa_bwd_tc_plan(const sf_window_attn_params* p) {
     WaBwdPlan w{};
@@ -778,28 +794,32 @@ static WaBwdPlan wa_bwd_tc_plan(const sf_window_attn_params* p) {
     bool nq, nkv;
     wa_bwd_ln_plan(p, &nq, &nkv, &w.share);
     Carver pc;
-    w.wq = plan_packed(pc, inner, C); w.wk = plan_packed(pc, inner, C); w.wv = plan_packed(pc, inner, C);   // q, k, v = n W^T + b
-    w.wot = plan_packed(pc, inner, C);                                                                       // g_O = gout W_o
-    w.wqt = plan_packed(pc, C, inner); w.wkt = plan_packed(pc, C, inner); w.wvt = plan_packed(pc, C, inner); // g_n = dQ W_q + ...
+    if (w.share) {
+        w.wqkv = plan_packed(pc, 3 * inner, C);     // q | k | v = n [Wq; Wk; Wv]^T + b
+        w.wqkvt = plan_packed(pc, C, 3 * inner);    // g_n = [dQ | dK | dV] [Wq; Wk; Wv]
+    } else {
+        w.wq = plan_packed(pc, inner, C); w.wkv = plan_packed(pc, 2 * inner, C);
+        w.wqt = plan_packed(pc, C, inner); w.wkvt = plan_packed(pc, C, 2 * inner);
+    }
+    w.wot = plan_packed(pc, inner, C);              // g_O = gout W_o
     Carver c;
     w.off_pk = c.take(pc.off);
     w.off_nq = c.take(tiled_bytes(M, C));
     w.off_nkv = c.take(w.share ? 0 : tiled_bytes(M, C));
     w.off_g = c.take(tiled_bytes(M, C));
     w.off_o = c.take(tiled_bytes(M, inner));
-    w.off_dq = c.take(tiled_bytes(M, inner));
-    w.off_dk = c.take(tiled_bytes(M, inner));
-    w.off_dv = c.take(tiled_bytes(M, inner));
-    w.off_f32 = c.take(8 * align_up((size_t)M * inner * sizeof(float)));
+    w.off_dqkv = c.take(tiled_bytes(M, 3 * inner));
+    w.off_f32 = c.take(align_up((size_t)M * 8 * inner * sizeof(float)));
     w.off_gn = c.take(2 * align_up((size_t)M * C * sizeof(float)));
     w.total = c.off;
     return w;
 }
 static bool wa_bwd_tc_ok(const sf_window_attn_params* p) {
     const int inner = p->num_heads * p->head_dim;
-    return bwd_tc_enabled() && p->C % 4 == 0 && (int)tc::pad16((uint32_t)p->C) <= TC_MAX_KPAD && inner % 4 == 0 &&
-           (int)tc::pad16((uint32_t)inner) <= TC_MAX_KPAD && aligned16(p->q_src) && aligned16(p->kv_src) &&
-           (long long)p->B * p->Hp * p->Wp < 2147483647LL;
+    const long long M = (long long)p->B * p->Hp * p->Wp;
+    return bwd_tc_enabled() && p->C % 4 == 0 && (int)tc::pad16((uint32_t)p->C) <= TC_MAX_KPAD && inner % 8 == 0 &&
+           (int)tc::pad16((uint32_t)inner) <= TC_MAX_KPAD && aligned16(p->q_src) && aligned16(p->kv_src) && M < 2147483647LL &&
+           M * 8 * inner < (1LL << 32);
 }
 static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
                                 const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st, bool mma,
@@ -807,7 +827,7 @@ static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, 
 static int window_attn_bwd_tc(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
     const sf_window_attn_params* p = &bp->fwd;
     const long long M = (long long)p->B * p->Hp * p->Wp;
-    const int C = p->C, inner = p->num_heads * p->head_dim;
+    const int C = p->C, inner = p->num_heads * p->head_dim, ld = 8 * inner;
     const WaBwdPlan w = wa_bwd_tc_plan(p);
     if (ws_bytes < w.total || !ws_ptr) { set_error("sf_window_attn_bwd: workspace too small (%zu B given, %zu needed)", ws_bytes, w.total); return SF_ERR_WORKSPACE; }
     char* base = reinterpret_cast<char*>(ws_ptr);
@@ -816,67 +836,107 @@ static int window_attn_bwd_tc(const sf_window_attn_bwd_params* bp, void* ws_ptr,
     bf16* nkv_t = w.share ? nq_t : reinterpret_cast<bf16*>(base + w.off_nkv);
     bf16* g_t = reinterpret_cast<bf16*>(base + w.off_g);
     bf16* o_t = reinterpret_cast<bf16*>(base + w.off_o);
-    bf16* dq_t = reinterpret_cast<bf16*>(base + w.off_dq);
-    bf16* dk_t = reinterpret_cast<bf16*>(base + w.off_dk);
-    bf16* dv_t = reinterpret_cast<bf16*>(base + w.off_dv);
-    const size_t fs = align_up((size_t)M * inner * sizeof(float)), cs = align_up((size_t)M * C * sizeof(float));
-    float* Q = reinterpret_cast<float*>(base + w.off_f32);
-    float* K = reinterpret_cast<float*>(base + w.off_f32 + fs);
-    float* V = reinterpret_cast<float*>(base + w.off_f32 + 2 * fs);
-    float* O = reinterpret_cast<float*>(base + w.off_f32 + 3 * fs);
-    float* gO = reinterpret_cast<float*>(base + w.off_f32 + 4 * fs);
-    float* dQ = reinterpret_cast<float*>(base + w.off_f32 + 5 * fs);
-    float* dK = reinterpret_cast<float*>(base + w.off_f32 + 6 * fs);
-    float* dV = reinterpret_cast<float*>(base + w.off_f32 + 7 * fs);
+    bf16* dqkv_t = reinterpret_cast<bf16*>(base + w.off_dqkv);
+    float* F = reinterpret_cast<float*>(base + w.off_f32);
+    float *Q = F, *K = F + inner, *V = F + 2 * inner, *gO = F + 3 * inner, *O = F + 4 * inner, *dQ = F + 5 * inner, *dK = F + 6 * inner,
+          *dV = F + 7 * inner;
+    const size_t cs = align_up((size_t)M * C * sizeof(float));
     float* gnq = reinterpret_cast<float*>(base + w.off_gn);
     float* gnkv = reinterpret_cast<float*>(base + w.off_gn + cs);
     bool need_q, need_kv, share;
     wa_bwd_ln_plan(p, &need_q, &need_kv, &share);
     const bool self_src = p->kv_src == p->q_src;
     SF_CHECK_ARG(share || bp->g_kv_src || self_src, "sf_window_attn_bwd: g_kv_src is required for cross attention");
+    const float* Wqkv[3] = {p->wq, p->wk, p->wv};
+    const float* bqkv[3] = {p->bq, p->bk, p->bv};
     PackJobs jobs{};
-    pack_fwd(jobs, p->wq, p->bq, inner, C, w.wq, pk);
-    pack_fwd(jobs, p->wk, p->bk, inner, C, w.wk, pk);
-    pack_fwd(jobs, p->wv, p->bv, inner, C, w.wv, pk);
+    if (share) {
+        pack_fwd_stack(jobs, 3, Wqkv, bqkv, inner, C, w.wqkv, pk);
+        pack_tr_stack(jobs, 3, Wqkv, inner, C, w.wqkvt, pk);
+    } else {
+        pack_fwd(jobs, p->wq, p->bq, inner, C, w.wq, pk);
+        pack_fwd_stack(jobs, 2, Wqkv + 1, bqkv + 1, inner, C, w.wkv, pk);
+        pack_tr(jobs, p->wq, inner, C, w.wqt, pk);
+        pack_tr_stack(jobs, 2, Wqkv + 1, inner, C, w.wkvt, pk);
+    }
     pack_tr(jobs, p->wo, C, inner, w.wot, pk);
-    pack_tr(jobs, p->wq, inner, C, w.wqt, pk);
-    pack_tr(jobs, p->wk, inner, C, w.wkt, pk);
-    pack_tr(jobs, p->wv, inner, C, w.wvt, pk);
     SF_TRY(launch_pack_jobs(jobs, st));
-    // ---- recompute the forward: normalised operands (bf16 tiles), q / k / v (fp32 rows for the attention-core adjoint) --------
+    // a GEMM whose fp32 output is a column block of F
+    auto gemm_to_F = [&](const bf16* A, const PackedGemm& g, int N, float* out, const char* name) -> int {
+        TcGemm t{};
+        t.A = A; t.M = M; t.K = C; t.a_mode = AM_TILED;
+        bind_packed(t, g, pk);
+        t.N = N; t.out_mode = OUT_F32; t.out = out; t.ldo = ld;
+        SF_TRY(tc_gemm_plan(&t));
+        return launch_tc_gemm(t, name, st);
+    };
+    // ---- recompute the forward: normalised operands (bf16 tiles), q | k | v (fp32, for the attention-core adjoint) -------------
     SF_TRY(launch_ln_to_tiled(p->q_src, p->ln_q_gamma, p->ln_q_beta, nq_t, M, C, p->ln_eps, st));
-    if (!share) SF_TRY(launch_ln_to_tiled(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, nkv_t, M, C, p->ln_eps, st));
-    SF_TRY(tc_gemm_tiled(nq_t, M, C, inner, w.wq, pk, true, false, Q, false, nullptr, nullptr, "bwd_tc_recompute_qkv", st));
-    SF_TRY(tc_gemm_tiled(nkv_t, M, C, inner, w.wk, pk, true, false, K, false, nullptr, nullptr, "bwd_tc_recompute_qkv", st));
-    SF_TRY(tc_gemm_tiled(nkv_t, M, C, inner, w.wv, pk, true, false, V, false, nullptr, nullptr, "bwd_tc_recompute_qkv", st));
+    if (share) {
+        SF_TRY(gemm_to_F(nq_t, w.wqkv, 3 * inner, Q, "bwd_tc_recompute_qkv"));
+    } else {
+        SF_TRY(launch_ln_to_tiled(p->kv_src, p->ln_kv_gamma, p->ln_kv_beta, nkv_t, M, C, p->ln_eps, st));
+        SF_TRY(gemm_to_F(nq_t, w.wq, inner, Q, "bwd_tc_recompute_qkv"));
+        SF_TRY(gemm_to_F(nkv_t, w.wkv, 2 * inner, K, "bwd_tc_recompute_qkv"));
+    }
     WinGeom geom = make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift);
-    const bool fused_o = attn_core_bwd_mma_supported(geom, p->head_dim, p->num_heads);
-    if (!fused_o) SF_TRY(launch_attn_core_f32(Q, K, V, O, p->bias_table, geom, inner, p->num_heads, p->head_dim, st));
+    SF_CHECK_ARG(attn_core_bwd_mma_supported(geom, p->head_dim, p->num_heads), "sf_window_attn_bwd: head shape not built for the tensor-core adjoint");
     // ---- output projection: gradient w.r.t. O ---------------------------------------------------------------------------------
     SF_TRY(launch_ln_to_tiled(bp->gout, nullptr, nullptr, g_t, M, C, 0.f, st));
-    SF_TRY(tc_gemm_tiled(g_t, M, C, inner, w.wot, pk, false, false, gO, false, nullptr, nullptr, "bwd_tc_dx_proj", st));
-    // ---- attention core -------------------------------------------------------------------------------------------------------
-    SF_TRY(launch_attn_core_bwd(Q, K, V, gO, dQ, dK, dV, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, true,
-                                fused_o ? O : nullptr));
-    SF_TRY(launch_ln_to_tiled(O, nullptr, nullptr, o_t, M, inner, 0.f, st));
-    SF_TRY(launch_ln_to_tiled(dQ, nullptr, nullptr, dq_t, M, inner, 0.f, st));
-    SF_TRY(launch_ln_to_tiled(dK, nullptr, nullptr, dk_t, M, inner, 0.f, st));
-    SF_TRY(launch_ln_to_tiled(dV, nullptr, nullptr, dv_t, M, inner, 0.f, st));
+    {
+        TcGemm t{};
+        t.A = g_t; t.M = M; t.K = C; t.a_mode = AM_TILED;
+        bind_packed(t, w.wot, pk);
+        t.bias = nullptr;
+        t.N = inner; t.out_mode = OUT_F32; t.out = gO; t.ldo = ld;
+        SF_TRY(tc_gemm_plan(&t));
+        SF_TRY(launch_tc_gemm(t, "bwd_tc_dx_proj", st));
+    }
+    // ---- attention core (fp16 mma.sync adjoint; also delivers O = P V) ---------------------------------------------------------------
+    SF_TRY(launch_attn_core_bwd_mma(Q, K, V, gO, dQ, dK, dV, O, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, ld));
+    SF_TRY(launch_ln_to_tiled(O, nullptr, nullptr, o_t, M, inner, 0.f, st, nullptr, ld));
+    const int nkc3 = (int)tc::pad16((uint32_t)(3 * inner)) / 8;
+    if (3 * inner <= TC_MAX_KPAD) {
+        SF_TRY(launch_ln_to_tiled(dQ, nullptr, nullptr, dqkv_t, M, 3 * inner, 0.f, st, nullptr, ld));
+    } else {   // rows wider than one cast launch takes: three launches into the chunk ranges of the same tiled tensor
+        for (int s = 0; s < 3; s++)
+            SF_TRY(launch_ln_to_tiled(dQ + s * inner, nullptr, nullptr, dqkv_t, M, inner, 0.f, st, nullptr, ld, nkc3, s * (inner / 8)));
+    }
     // ---- weight gradients -------------------------------------------------------------------------------------------------------
     SF_TRY(launch_tc_wgrad(g_t, o_t, bp->g_wo, bp->g_bo, M, C, inner, "bwd_tc_wgrad", st));
-    SF_TRY(launch_tc_wgrad(dq_t, nq_t, bp->g_wq, bp->g_bq, M, inner, C, "bwd_tc_wgrad", st));
-    SF_TRY(launch_tc_wgrad(dk_t, nkv_t, bp->g_wk, bp->g_bk, M, inner, C, "bwd_tc_wgrad", st));
-    SF_TRY(launch_tc_wgrad(dv_t, nkv_t, bp->g_wv, bp->g_bv, M, inner, C, "bwd_tc_wgrad", st));
-    // ---- gradients w.r.t. the (normalised) operands ---------------------------------------------------------------------------------
-    float* gq_dst = need_q ? gnq : bp->g_q_src;
-    SF_TRY(tc_gemm_tiled(dq_t, M, inner, C, w.wqt, pk, false, false, gq_dst, false, nullptr, nullptr, "bwd_tc_dx_qkv", st));
     if (share) {
-        SF_TRY(tc_gemm_tiled(dk_t, M, inner, C, w.wkt, pk, false, false, gq_dst, true, nullptr, nullptr, "bwd_tc_dx_qkv", st));
-        SF_TRY(tc_gemm_tiled(dv_t, M, inner, C, w.wvt, pk, false, false, gq_dst, true, nullptr, nullptr, "bwd_tc_dx_qkv", st));
+        TcWgradArgs a{};
+        a.G = dqkv_t; a.A = nq_t; a.M = M; a.N = 3 * inner; a.K = C; a.nout = 3;
+        a.Wg[0] = bp->g_wq; a.Wg[1] = bp->g_wk; a.Wg[2] = bp->g_wv;
+        a.bias_grad[0] = bp->g_bq; a.bias_grad[1] = bp->g_bk; a.bias_grad[2] = bp->g_bv;
+        SF_TRY(launch_tc_wgrad_ex(a, "bwd_tc_wgrad", st));
+    } else {
+        TcWgradArgs a{};
+        a.G = dqkv_t; a.A = nq_t; a.M = M; a.N = inner; a.K = C; a.nout = 1; a.g_tile_nkc = nkc3; a.g_kc0 = 0;
+        a.Wg[0] = bp->g_wq; a.bias_grad[0] = bp->g_bq;
+        SF_TRY(launch_tc_wgrad_ex(a, "bwd_tc_wgrad", st));
+        TcWgradArgs b2{};
+        b2.G = dqkv_t; b2.A = nkv_t; b2.M = M; b2.N = 2 * inner; b2.K = C; b2.nout = 2; b2.g_tile_nkc = nkc3; b2.g_kc0 = inner / 8;
+        b2.Wg[0] = bp->g_wk; b2.Wg[1] = bp->g_wv; b2.bias_grad[0] = bp->g_bk; b2.bias_grad[1] = bp->g_bv;
+        SF_TRY(launch_tc_wgrad_ex(b2, "bwd_tc_wgrad", st));
+    }
+    // ---- gradients w.r.t. the (normalised) operands: K-concatenated GEMMs over [dQ | dK | dV] ---------------------------------------
+    auto gemm_dx = [&](int kc0, int K, const PackedGemm& g, float* out) -> int {
+        TcGemm t{};
+        t.A = dqkv_t; t.M = M; t.K = K; t.a_mode = AM_TILED; t.a_tile_nkc = nkc3; t.a_kc0 = kc0;
+        bind_packed(t, g, pk);
+        t.bias = nullptr;
+        t.N = C; t.out_mode = OUT_F32; t.out = out; t.ldo = C;
+        SF_TRY(tc_gemm_plan(&t));
+        return launch_tc_gemm(t, "bwd_tc_dx_qkv", st);
+    };
+    float* gq_dst = need_q ? gnq : bp->g_q_src;
+    if (share) {
+        SF_TRY(gemm_dx(0, 3 * inner, w.wqkvt, gq_dst));
     } else {
         float* gkv_dst = need_kv ? gnkv : (bp->g_kv_src ? bp->g_kv_src : gnkv);
-        SF_TRY(tc_gemm_tiled(dk_t, M, inner, C, w.wkt, pk, false, false, gkv_dst, false, nullptr, nullptr, "bwd_tc_dx_qkv", st));
-        SF_TRY(tc_gemm_tiled(dv_t, M, inner, C, w.wvt, pk, false, false, gkv_dst, true, nullptr, nullptr, "bwd_tc_dx_qkv", st));
+        SF_TRY(gemm_dx(0, inner, w.wqt, gq_dst));
+        SF_TRY(gemm_dx(inner / 8, 2 * inner, w.wkvt, gkv_dst));
     }
     // ---- LayerNorm adjoints (as in the exact path) ----------------------------------------------------------------------------------
     if (need_q) SF_TRY(launch_ln_bwd(p->q_src, p->ln_q_gamma, p->ln_q_beta, gnq, bp->g_q_src, bp->g_ln_q_gamma, bp->g_ln_q_beta, M, C, p->ln_eps, false, bp->add_to_g_q_src, st));
@@ -906,7 +966,9 @@ static inline void wa_bwd_ln_plan(const sf_window_attn_params* p, bool* need_q, 
 
 size_t window_attn_bwd_ws(const sf_window_attn_bwd_params* bp) {
     const sf_window_attn_params* p = &bp->fwd;
-    if (p->precision == SF_PREC_BF16 && wa_bwd_tc_ok(p)) return wa_bwd_tc_plan(p).total;
+    if (p->precision == SF_PREC_BF16 && wa_bwd_tc_ok(p) &&
+        attn_core_bwd_mma_supported(make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift), p->head_dim, p->num_heads))
+        return wa_bwd_tc_plan(p).total;
     const size_t M = (size_t)p->B * p->Hp * p->Wp, inner = (size_t)p->num_heads * p->head_dim;
     return 8 * align_up(M * inner * sizeof(float)) + 4 * align_up(M * p->C * sizeof(float));
 }
@@ -914,7 +976,8 @@ size_t window_attn_bwd_ws(const sf_window_attn_bwd_params* bp) {
 int window_attn_bwd(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
     const bool tf = bp->fwd.precision == SF_PREC_BF16;   // bf16 operators: tensor-core GEMMs in the backward pass
     const sf_window_attn_params* p = &bp->fwd;
-    if (tf && wa_bwd_tc_ok(p)) return window_attn_bwd_tc(bp, ws_ptr, ws_bytes, st);
+    if (tf && wa_bwd_tc_ok(p) && attn_core_bwd_mma_supported(make_geom(p->B, p->Hp, p->Wp, p->wsh, p->wsw, p->shift), p->head_dim, p->num_heads))
+        return window_attn_bwd_tc(bp, ws_ptr, ws_bytes, st);
     const long long M = (long long)p->B * p->Hp * p->Wp;
     const int C = p->C, inner = p->num_heads * p->head_dim;
     Workspace ws(ws_ptr, ws_bytes);

@@ -472,10 +472,20 @@ static constexpr int HEAD_THREADS = 256;
 static constexpr int HEAD_MAXK = 7;
 
 // conv1 -> t[b][r][c][2]; when STATS, per-block partial (sum0,sum1,sq0,sq1) -> partials[block][4]
-template <bool STATS>
+// ELU(alpha = 1) with the exponential on ex2.approx (2^-22 relative): the head applies it 2 (eval) or 18 (train) times per pixel
+__device__ __forceinline__ float head_elu(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    return v > 0.f ? v : e - 1.f;
+}
+
+// KS: compile-time kernel size (0 = use the run-time `ks`).  ACT (eval mode, running statistics): the BatchNorm affine
+// (computed beforehand by k_head_bn_affine) and the ELU are applied here, once per pixel, and conv2 reads activations.
+template <bool STATS, int KS, bool ACT>
 __global__ void k_head_conv1(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w1,
                              const float* __restrict__ b1, float2* __restrict__ t, float* __restrict__ partials,
-                             int B, int H, int W, int ks) {
+                             const float* __restrict__ affine, int B, int H, int W, int ks_rt) {
+    const int ks = KS ? KS : ks_rt;
     __shared__ float wsm[2 * 2 * HEAD_MAXK * HEAD_MAXK];
     __shared__ float red[4][HEAD_THREADS / 32];
     for (int i = threadIdx.x; i < 4 * ks * ks; i += blockDim.x) wsm[i] = w1[i];
@@ -491,8 +501,10 @@ __global__ void k_head_conv1(const float* __restrict__ x, const float* __restric
         const float* xb = x + b * H * W;
         const float* yb = y + b * H * W;
         float o0 = b1[0], o1 = b1[1];
+#pragma unroll
         for (int dr = 0; dr < ks; dr++) {
             int rr = reflect_both(r + dr - pad, H);
+#pragma unroll
             for (int dc = 0; dc < ks; dc++) {
                 int cc = reflect_both(c + dc - pad, W);
                 float xv = xb[(long long)rr * W + cc], yv = yb[(long long)rr * W + cc];
@@ -504,6 +516,7 @@ __global__ void k_head_conv1(const float* __restrict__ x, const float* __restric
                 o1 = fmaf(wsm[(1 * 2 + 1) * ks * ks + wi], yv, o1);
             }
         }
+        if (ACT) { o0 = head_elu(fmaf(o0, affine[0], affine[1])); o1 = head_elu(fmaf(o1, affine[2], affine[3])); }
         t[i] = make_float2(o0, o1);
         if (STATS) { s0 += o0; s1 += o1; q0 += o0 * o0; q1 += o1 * o1; }
     }
@@ -559,8 +572,12 @@ __global__ void k_head_bn_affine(const float* __restrict__ partials, int nblocks
     }
 }
 
+// ACT: t holds conv1 outputs, BatchNorm affine + ELU are applied per tap (train mode: the statistics come after conv1);
+// !ACT: t already holds activations
+template <int KS, bool ACT>
 __global__ void k_head_conv2(const float2* __restrict__ t, const float* __restrict__ affine, const float* __restrict__ w2,
-                             const float* __restrict__ b2, float* __restrict__ out, int B, int H, int W, int ks) {
+                             const float* __restrict__ b2, float* __restrict__ out, int B, int H, int W, int ks_rt) {
+    const int ks = KS ? KS : ks_rt;
     __shared__ float wsm[2 * HEAD_MAXK * HEAD_MAXK];
     for (int i = threadIdx.x; i < 2 * ks * ks; i += blockDim.x) wsm[i] = w2[i];
     __syncthreads();
@@ -574,12 +591,14 @@ __global__ void k_head_conv2(const float2* __restrict__ t, const float* __restri
         long long b = p / H;
         const float2* tb = t + b * H * W;
         float o = b2[0];
+#pragma unroll
         for (int dr = 0; dr < ks; dr++) {
             int rr = reflect_both(r + dr - pad, H);
+#pragma unroll
             for (int dc = 0; dc < ks; dc++) {
                 int cc = reflect_both(c + dc - pad, W);
                 float2 v = tb[(long long)rr * W + cc];
-                float a0 = elu1(fmaf(v.x, sc0, sh0)), a1 = elu1(fmaf(v.y, sc1, sh1));
+                float a0 = ACT ? head_elu(fmaf(v.x, sc0, sh0)) : v.x, a1 = ACT ? head_elu(fmaf(v.y, sc1, sh1)) : v.y;
                 o = fmaf(wsm[dr * ks + dc], a0, o);
                 o = fmaf(wsm[ks * ks + dr * ks + dc], a1, o);
             }
@@ -739,13 +758,28 @@ int head_fwd(const sf_head_params* p, void* ws_ptr, size_t ws_bytes, cudaStream_
     float* affine = ws.take<float>(4);
     if (!t || !partials || !affine) { set_error("sf_head_fwd: workspace too small (%zu B given)", ws_bytes); return SF_ERR_WORKSPACE; }
     ProfScope ps("final_head", (double)total * (4.0 * 2 * p->ksize * p->ksize + 2.0 * 2 * p->ksize * p->ksize), 12.0 * (double)total, st);
-    if (p->training) k_head_conv1<true><<<nb, HEAD_THREADS, 0, st>>>(p->x, p->y, p->w1, p->b1, t, partials, p->B, p->H, p->W, p->ksize);
-    else k_head_conv1<false><<<nb, HEAD_THREADS, 0, st>>>(p->x, p->y, p->w1, p->b1, t, partials, p->B, p->H, p->W, p->ksize);
-    SF_CHECK_LAUNCH("head_conv1");
-    k_head_bn_affine<<<1, 128, 0, st>>>(partials, nb, total, p->bn_gamma, p->bn_beta, p->running_mean, p->running_var,
-                                        p->save_mean, p->save_invstd, affine, p->bn_eps, p->bn_momentum, p->training);
-    SF_CHECK_LAUNCH("head_bn_affine");
-    k_head_conv2<<<nb, HEAD_THREADS, 0, st>>>(t, affine, p->w2, p->b2, p->out, p->B, p->H, p->W, p->ksize);
+    const bool k3 = p->ksize == 3;
+    if (p->training) {
+        // batch statistics: conv1 (+ partial sums) -> scale / shift -> conv2 applies BatchNorm + ELU per tap
+        if (k3) k_head_conv1<true, 3, false><<<nb, HEAD_THREADS, 0, st>>>(p->x, p->y, p->w1, p->b1, t, partials, nullptr, p->B, p->H, p->W, 3);
+        else k_head_conv1<true, 0, false><<<nb, HEAD_THREADS, 0, st>>>(p->x, p->y, p->w1, p->b1, t, partials, nullptr, p->B, p->H, p->W, p->ksize);
+        SF_CHECK_LAUNCH("head_conv1");
+        k_head_bn_affine<<<1, 128, 0, st>>>(partials, nb, total, p->bn_gamma, p->bn_beta, p->running_mean, p->running_var,
+                                            p->save_mean, p->save_invstd, affine, p->bn_eps, p->bn_momentum, 1);
+        SF_CHECK_LAUNCH("head_bn_affine");
+        if (k3) k_head_conv2<3, true><<<nb, HEAD_THREADS, 0, st>>>(t, affine, p->w2, p->b2, p->out, p->B, p->H, p->W, 3);
+        else k_head_conv2<0, true><<<nb, HEAD_THREADS, 0, st>>>(t, affine, p->w2, p->b2, p->out, p->B, p->H, p->W, p->ksize);
+    } else {
+        // running statistics: scale / shift first, BatchNorm + ELU once per pixel inside conv1, conv2 reads activations
+        k_head_bn_affine<<<1, 128, 0, st>>>(partials, nb, total, p->bn_gamma, p->bn_beta, p->running_mean, p->running_var,
+                                            p->save_mean, p->save_invstd, affine, p->bn_eps, p->bn_momentum, 0);
+        SF_CHECK_LAUNCH("head_bn_affine");
+        if (k3) k_head_conv1<false, 3, true><<<nb, HEAD_THREADS, 0, st>>>(p->x, p->y, p->w1, p->b1, t, partials, affine, p->B, p->H, p->W, 3);
+        else k_head_conv1<false, 0, true><<<nb, HEAD_THREADS, 0, st>>>(p->x, p->y, p->w1, p->b1, t, partials, affine, p->B, p->H, p->W, p->ksize);
+        SF_CHECK_LAUNCH("head_conv1");
+        if (k3) k_head_conv2<3, false><<<nb, HEAD_THREADS, 0, st>>>(t, affine, p->w2, p->b2, p->out, p->B, p->H, p->W, 3);
+        else k_head_conv2<0, false><<<nb, HEAD_THREADS, 0, st>>>(t, affine, p->w2, p->b2, p->out, p->B, p->H, p->W, p->ksize);
+    }
     SF_CHECK_LAUNCH("head_conv2");
     return SF_OK;
 }

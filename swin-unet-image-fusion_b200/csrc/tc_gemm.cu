@@ -166,15 +166,23 @@ __global__ void k_pack_jobs(PackJobs jobs) {
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 const int k = jk * j.KR + kc * 8 + e;
-                v[e] = k < j.K ? (j.transposed ? j.w[(long long)k * j.N + n] : j.w[(long long)n * j.K + k]) : 0.f;
+                float x = 0.f;
+                if (k < j.K) {
+                    if (j.transposed) { const int s = k / j.each; x = j.w[s][(long long)(k - s * j.each) * j.N + n]; }   // sources stacked along K
+                    else { const int s = n / j.each; x = j.w[s][(long long)(n - s * j.each) * j.K + k]; }               // stacked along N
+                }
+                v[e] = x;
             }
 #pragma unroll
             for (int e = 0; e < 4; e++) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
         }
         *reinterpret_cast<uint4*>(j.out + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < j.n_chunks * j.NR; n += gridDim.x * blockDim.x)
-        j.bias_out[n] = (n < j.N && j.b) ? j.b[n] : 0.f;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < j.n_chunks * j.NR; n += gridDim.x * blockDim.x) {
+        float b = 0.f;
+        if (n < j.N && !j.transposed) { const int s = n / j.each; if (j.b[s]) b = j.b[s][n - s * j.each]; }
+        j.bias_out[n] = b;
+    }
 }
 
 int launch_pack_jobs(const PackJobs& jobs, cudaStream_t st) {
@@ -433,13 +441,14 @@ __device__ __forceinline__ void produce_a_merge(uint8_t* sA, const TcGemm& p, lo
 // =============================================================================================
 template <int LPR>
 __global__ void __launch_bounds__(256) k_ln_to_tiled(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                     bf16* __restrict__ out, long long M, int C, int Kpad, float eps, int gather, WinOrder wo) {
+                                                     bf16* __restrict__ out, long long M, int C, int Kpad, float eps, int gather, WinOrder wo,
+                                                     long long ld_in, int out_nkc, int out_kc0) {
     // LPR lanes per row, three float4 per lane (C <= 12 * LPR), 32 / LPR rows per warp.
     // gamma == nullptr: no LayerNorm, a plain fp32 -> bf16 cast into the tiled layout (backward pass operands).
     // Rows M .. 128*ceil(M/128)-1 of the last tile are written as zeros: the weight-gradient GEMM sums over token rows.
     const int lane = threadIdx.x & 31, l = lane & (LPR - 1), sub = lane / LPR;
     constexpr int RPW = 32 / LPR;
-    const int nf4 = C >> 2, nslots = Kpad >> 2, nkc = Kpad >> 3;
+    const int nf4 = C >> 2, nslots = Kpad >> 2;
     const long long Mpad = (M + 127) / 128 * 128;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(256) k_ln_to_tiled(const float* __restrict__ i
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             int q = l + LPR * i;
-            v[i] = (real && q < nf4) ? *reinterpret_cast<const float4*>(in + srow * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = (real && q < nf4) ? *reinterpret_cast<const float4*>(in + srow * ld_in + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float mean = 0.f, rstd = 1.f;
         if (gamma) {
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(256) k_ln_to_tiled(const float* __restrict__ i
                         pk = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
                     }
                 }
-                *reinterpret_cast<uint2*>(out + ((tile * nkc + (q >> 1)) * 128 + r) * 8 + (q & 1) * 4) = pk;
+                *reinterpret_cast<uint2*>(out + ((tile * out_nkc + out_kc0 + (q >> 1)) * 128 + r) * 8 + (q & 1) * 4) = pk;
             }
         }
     }
@@ -502,13 +511,13 @@ __global__ void __launch_bounds__(256) k_ln_to_tiled(const float* __restrict__ i
 template <int NF4>
 __global__ void __launch_bounds__(256) k_ln_to_tiled_rows(const float* __restrict__ in, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, bf16* __restrict__ out, long long M, int C, int Kpad,
-                                                          float eps, int gather, WinOrder wo) {
+                                                          float eps, int gather, WinOrder wo, long long ld_in, int out_nkc, int out_kc0) {
     const int nf4 = C >> 2, nkc = Kpad >> 3;
     const long long Mpad = (M + 127) / 128 * 128;
     for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < Mpad; row += (long long)gridDim.x * blockDim.x) {
         const bool real = row < M;
         const long long srow = (gather && real) ? win_order_token(wo, (uint32_t)row) : row;
-        const float4* src = reinterpret_cast<const float4*>(in + srow * C);
+        const float4* src = reinterpret_cast<const float4*>(in + srow * ld_in);
         float4 v[NF4];
 #pragma unroll
         for (int i = 0; i < NF4; i++) v[i] = (real && i < nf4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(256) k_ln_to_tiled_rows(const float* __restric
 #pragma unroll
         for (int c = 0; c < NF4 / 2; c++) {
             if (c < nkc)
-                *reinterpret_cast<uint4*>(out + ((tile * nkc + c) * 128 + r) * 8) =
+                *reinterpret_cast<uint4*>(out + ((tile * out_nkc + out_kc0 + c) * 128 + r) * 8) =
                     make_uint4(pack_bf16x2(v[2 * c].x, v[2 * c].y), pack_bf16x2(v[2 * c].z, v[2 * c].w),
                                pack_bf16x2(v[2 * c + 1].x, v[2 * c + 1].y), pack_bf16x2(v[2 * c + 1].z, v[2 * c + 1].w));
         }
@@ -551,8 +560,11 @@ __global__ void __launch_bounds__(256) k_ln_to_tiled_rows(const float* __restric
 }
 
 int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, bf16* out, long long M, int C, float eps, cudaStream_t st,
-                       const WinOrder* wo) {
+                       const WinOrder* wo, long long ld_in, int out_nkc, int out_kc0) {
     const int Kpad = (int)pad16((uint32_t)C);
+    if (ld_in <= 0) ld_in = C;
+    if (out_nkc <= 0) { out_nkc = Kpad >> 3; out_kc0 = 0; }
+    SF_CHECK_ARG(ld_in % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) & 15) == 0), "ln_to_tiled: rows must be 16-byte aligned");
     SF_CHECK_ARG(C % 4 == 0 && Kpad <= TC_MAX_KPAD, "ln_to_tiled: unsupported row width %d", C);
     long long blocks = (M * 32 + 255) / 256;
     if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
@@ -563,20 +575,20 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
         long long rb = (M + 255) / 256;
         if (rb > (long long)sm_count() * 8) rb = (long long)sm_count() * 8;
         if (rb < 1) rb = 1;
-        if (Kpad <= 32) k_ln_to_tiled_rows<8><<<(unsigned)rb, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
-        else k_ln_to_tiled_rows<16><<<(unsigned)rb, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{});
+        if (Kpad <= 32) k_ln_to_tiled_rows<8><<<(unsigned)rb, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{}, ld_in, out_nkc, out_kc0);
+        else k_ln_to_tiled_rows<16><<<(unsigned)rb, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, wo ? *wo : WinOrder{}, ld_in, out_nkc, out_kc0);
         SF_CHECK_LAUNCH("ln_to_tiled");
         return SF_OK;
     }
     const WinOrder woa = wo ? *wo : WinOrder{};
     if (Kpad <= 96) {
         blocks = std::min<long long>((M / 4 * 32 + 255) / 256 + 1, (long long)sm_count() * 16);
-        k_ln_to_tiled<8><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa);
+        k_ln_to_tiled<8><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa, ld_in, out_nkc, out_kc0);
     } else if (Kpad <= 192) {
         blocks = std::min<long long>((M / 2 * 32 + 255) / 256 + 1, (long long)sm_count() * 16);
-        k_ln_to_tiled<16><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa);
+        k_ln_to_tiled<16><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa, ld_in, out_nkc, out_kc0);
     } else {
-        k_ln_to_tiled<32><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa);
+        k_ln_to_tiled<32><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa, ld_in, out_nkc, out_kc0);
     }
     SF_CHECK_LAUNCH("ln_to_tiled");
     return SF_OK;
@@ -745,7 +757,7 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                         mbar_arrive_expect_tx(&w_full[stg], L.slabW_bytes + L.slabA_bytes);
                         bulk_g2s(dstW, p.Wp + ((size_t)c * n_slabs + s) * (size_t)p.NCH * p.KS, L.slabW_bytes, &w_full[stg]);
                         if (STREAM) {
-                            const bf16* srcA = reinterpret_cast<const bf16*>(p.A) + ((size_t)tile * p.a_nkc + (size_t)s * (p.KS >> 3)) * 128 * 8;
+                            const bf16* srcA = reinterpret_cast<const bf16*>(p.A) + ((size_t)tile * p.a_tile_nkc + p.a_kc0 + (size_t)s * (p.KS >> 3)) * 128 * 8;
                             bulk_g2s(dstW + align128(L.slabW_bytes), srcA, L.slabA_bytes, &w_full[stg]);
                         }
                     }
@@ -901,6 +913,7 @@ int tc_gemm_plan(TcGemm* p) {
         if (p->a_mode != AM_MERGE) SF_CHECK_ARG(p->K % 4 == 0 && p->lda % 4 == 0, "tc_gemm: fp32 A needs K %% 4 == 0 (K=%d)", p->K);
     } else {
         p->a_nkc = p->Kpad >> 3;
+        if (p->a_tile_nkc <= 0) { p->a_tile_nkc = p->a_nkc; p->a_kc0 = 0; }   // else: A is a column range of a wider tiled tensor
     }
     SF_CHECK_ARG(!p->win_order || p->M < 2147483647LL, "tc_gemm: %lld rows exceed the window-order index range", p->M);
     const long long m_tiles = (p->M + 127) / 128;

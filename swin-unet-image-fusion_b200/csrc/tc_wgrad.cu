@@ -26,12 +26,15 @@ static constexpr uint32_t WG_GBYTES = 16 * WG_CHUNK;   // m-block of G: 128 feat
 static constexpr size_t WG_SMEM_LIMIT = 227 * 1024;
 
 struct TcWgrad {
-    const bf16* G; int g_nkc;     // gradient rows, tiled; g_nkc chunks per tile (= pad16(N) / 8)
+    const bf16* G; int g_nkc;     // gradient rows, tiled; g_nkc chunks of this operand per tile (= pad16(N) / 8)
     const bf16* A; int a_nkc;     // activation rows, tiled (= pad16(K) / 8 chunks)
+    int g_tile_nkc, g_kc0;        // G is the chunk range [g_kc0, g_kc0 + g_nkc) of a tiled tensor with g_tile_nkc chunks per tile
+    int a_tile_nkc, a_kc0;        // same for A
     long long M;                  // token rows
     int N, K;
-    float* Wg;                    // [N][K] fp32, accumulated
-    float* bias_grad;             // [N] fp32, accumulated; or null
+    int each;                     // rows [s*each, (s+1)*each) of the product go to Wg[s] / bias_grad[s] (stacked weight matrices)
+    float* Wg[3];                 // each [each][K] fp32, accumulated
+    float* bias_grad[3];          // each [each] fp32, accumulated; or null
     int m_blocks, n_blocks, nbc;  // nbc: chunks of A per n-block (<= 32)
     int splits;                   // token-range splits
     long long tiles, tiles_per_split;
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(TcWgrad p) {
     uint64_t* d_full = bars + 4;
     uint64_t* d_empty = bars + 5;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    const bool has_bias = p.bias_grad != nullptr;
+    const bool has_bias = p.bias_grad[0] != nullptr;
     const uint32_t ncols = p.ncols;
     const long long items = (long long)p.m_blocks * p.n_blocks * p.splits;
 
@@ -102,8 +105,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(TcWgrad p) {
                     mbar_wait(&empty[st], ((cnt >> 1) & 1u) ^ 1u);
                     uint8_t* dst = smem + st * stage_bytes;
                     mbar_arrive_expect_tx(&full[st], (gch + ach) * WG_CHUNK);
-                    bulk_g2s(dst, p.G + ((size_t)t * p.g_nkc + (size_t)mb * 16) * 1024, gch * WG_CHUNK, &full[st]);
-                    bulk_g2s(dst + WG_GBYTES, p.A + ((size_t)t * p.a_nkc + (size_t)nb * p.nbc) * 1024, ach * WG_CHUNK, &full[st]);
+                    bulk_g2s(dst, p.G + ((size_t)t * p.g_tile_nkc + p.g_kc0 + (size_t)mb * 16) * 1024, gch * WG_CHUNK, &full[st]);
+                    bulk_g2s(dst + WG_GBYTES, p.A + ((size_t)t * p.a_tile_nkc + p.a_kc0 + (size_t)nb * p.nbc) * 1024, ach * WG_CHUNK, &full[st]);
                 }
             }
         }
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(TcWgrad p) {
                 float v[16];
                 tmem_ld16(tl + (uint32_t)c16, v);
                 if (n < p.N) {
-                    float* dst = p.Wg + (size_t)n * p.K + k0 + c16;
+                    const int src = n / p.each;
+                    float* dst = p.Wg[src] + (size_t)(n - src * p.each) * p.K + k0 + c16;
                     if (p.vec4) {   // K % 4 == 0 and Wg 16-byte aligned: every group of four columns is one aligned vector
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(TcWgrad p) {
             if (has_bias && nb == 0) {
                 float v[16];
                 tmem_ld16(tl + p.bias_col, v);
-                if (n < p.N) atomicAdd(p.bias_grad + n, v[0]);
+                if (n < p.N) { const int src = n / p.each; atomicAdd(p.bias_grad[src] + (n - src * p.each), v[0]); }
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -182,11 +186,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(TcWgrad p) {
 }
 
 int launch_tc_wgrad(const bf16* G, const bf16* A, float* Wg, float* bias_grad, long long M, int N, int K, const char* name, cudaStream_t st) {
-    SF_CHECK_ARG(G && A && Wg && M > 0 && N > 0 && K > 0, "tc_wgrad: bad arguments");
+    TcWgradArgs a{};
+    a.G = G; a.A = A; a.M = M; a.N = N; a.K = K; a.nout = 1; a.Wg[0] = Wg; a.bias_grad[0] = bias_grad;
+    return launch_tc_wgrad_ex(a, name, st);
+}
+
+int launch_tc_wgrad_ex(const TcWgradArgs& a, const char* name, cudaStream_t st) {
+    const bf16* G = a.G; const bf16* A = a.A; const long long M = a.M; const int N = a.N, K = a.K;
+    float* Wg = a.Wg[0]; float* bias_grad = a.bias_grad[0];
+    SF_CHECK_ARG(G && A && Wg && M > 0 && N > 0 && K > 0 && a.nout >= 1 && a.nout <= 3 && N % a.nout == 0, "tc_wgrad: bad arguments");
     TcWgrad p{};
-    p.G = G; p.A = A; p.M = M; p.N = N; p.K = K; p.Wg = Wg; p.bias_grad = bias_grad;
+    p.G = G; p.A = A; p.M = M; p.N = N; p.K = K;
+    p.each = N / a.nout;
+    for (int i = 0; i < 3; i++) { p.Wg[i] = i < a.nout ? a.Wg[i] : nullptr; p.bias_grad[i] = i < a.nout ? a.bias_grad[i] : nullptr; }
+    SF_CHECK_ARG(!bias_grad || a.nout == 1 || (a.bias_grad[1] && (a.nout < 3 || a.bias_grad[2])), "tc_wgrad: bias gradients are all or none");
     p.g_nkc = (int)pad16((uint32_t)N) / 8;
     p.a_nkc = (int)pad16((uint32_t)K) / 8;
+    p.g_tile_nkc = a.g_tile_nkc > 0 ? a.g_tile_nkc : p.g_nkc; p.g_kc0 = a.g_tile_nkc > 0 ? a.g_kc0 : 0;
+    p.a_tile_nkc = a.a_tile_nkc > 0 ? a.a_tile_nkc : p.a_nkc; p.a_kc0 = a.a_tile_nkc > 0 ? a.a_kc0 : 0;
     p.m_blocks = (p.g_nkc + 15) / 16;
     p.n_blocks = (p.a_nkc + 31) / 32;
     p.nbc = (p.a_nkc + p.n_blocks - 1) / p.n_blocks;
@@ -198,7 +215,8 @@ int launch_tc_wgrad(const bf16* G, const bf16* A, float* Wg, float* bias_grad, l
     // (128 x nbc*8 reductions into Wg) is paid for by its streaming phase
     long long splits = ((long long)sm_count() + blocks - 1) / blocks;
     splits = std::max(1LL, std::min(splits, (p.tiles + 7) / 8));
-    p.vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wg) & 15) == 0);
+    p.vec4 = (K % 4 == 0);
+    for (int i = 0; i < a.nout; i++) p.vec4 = p.vec4 && ((reinterpret_cast<uintptr_t>(a.Wg[i]) & 15) == 0);
     p.tiles_per_split = (p.tiles + splits - 1) / splits;
     p.splits = (int)((p.tiles + p.tiles_per_split - 1) / p.tiles_per_split);
     const uint32_t stage_bytes = WG_GBYTES + (uint32_t)p.nbc * WG_CHUNK;

@@ -1,7 +1,20 @@
-"""BASELINE configs[4]: isolated window-attention microbenchmark at the five model shapes (B=64, 256x256 input) x
-{self, cross} x {plain, shifted}: device time of one fused operator call (LayerNorm + q|k|v GEMM + attention core +
-projection + residual), per kernel, against the algorithmic FLOPs 8NC^2 + 196NC and bytes.
-    python tools/bench_wa.py > profiles/<tag>_wa_microbench.json"""
+"""BASELINE configs[4]: isolated self / cross window-attention microbenchmark -- sweep of window size, heads, head width
+and token count against the roofline.
+
+    python tools/bench_wa.py [--quick] > profiles/<tag>_wa_microbench.json
+
+One row per (window, heads, head_dim, tokens, shift, cross): device time of ONE operator call (LayerNorm + q|k|v
+projection + attention core + output projection + residual, through the public ops.window_attention -> C ABI), CUDA
+events, L2-hot (back-to-back calls on the same tensors) and L2-flushed (a 512 MB write between calls), against
+
+    FLOPs = 8 N C^2 + 4 t N C        (t = window tokens; projections + QK^T + PV)
+    bytes = 4 N C (2 | 3)            (fp32 rows read once -- q source [+ k/v source] -- and written once: the ideal fusion)
+    roof  = max(FLOPs / bf16 tensor peak, bytes / HBM peak)   -> frac_of_roof = roof / measured
+
+The five model shapes at B = 64 (stage 0..4 of the default config) are always included.  Shapes the tensor-core path
+does not take (C % 4 != 0, C > 384) are skipped and listed.
+"""
+import argparse
 import json
 import os
 import sys
@@ -13,51 +26,100 @@ import torch  # noqa: E402
 
 import swinfuse  # noqa: E402
 
-STAGES = [(24, 133, 3), (48, 70, 6), (96, 35, 12), (192, 21, 24), (384, 14, 48)]
+MODEL_SHAPES = [(7, 8, 3, 64, 133), (7, 8, 6, 64, 70), (7, 8, 12, 64, 35), (7, 8, 24, 64, 21), (7, 8, 48, 64, 14)]
 PEAK_TF, PEAK_GBS = 1389.5, 6551.0
 if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     PEAK_TF, PEAK_GBS = pk["bf16_tflops_sustained"], pk["hbm_gbs"]
 
 
+def geometry(ws, tokens):
+    """(B, side) with side a multiple of ws and B * side^2 ~ tokens"""
+    side = ws * max(1, round((min(tokens, 133 * 133 * 4) ** 0.5) / ws))
+    side = min(side, ws * (266 // ws))
+    b = max(1, round(tokens / (side * side)))
+    return b, side
+
+
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true", help="model shapes and a thin slice of the sweep")
+    args = ap.parse_args()
     ops = swinfuse.ops
-    b, nh, reps = 64, 8, 5
     g = torch.Generator(device="cuda").manual_seed(0)
     r = lambda *s: torch.randn(*s, device="cuda", generator=g)
-    rows = []
-    for (c, hp, d) in STAGES:
-        x = r(b, c, hp, hp).contiguous(memory_format=torch.channels_last)
-        y = r(b, c, hp, hp).contiguous(memory_format=torch.channels_last)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    rows, skipped = [], []
+
+    def measure(ws, nh, d, b, side, shift, cross, tag):
+        c = nh * d
+        x = r(b, c, side, side).contiguous(memory_format=torch.channels_last)
+        y = r(b, c, side, side).contiguous(memory_format=torch.channels_last) if cross else None
         ln = (1 + 0.1 * r(c), 0.1 * r(c))
         w = lambda: torch.nn.Parameter(r(nh * d, c) * c ** -0.5)
         P = dict(wq=w(), bq=0.1 * r(nh * d), wk=w(), bk=0.1 * r(nh * d), wv=w(), bv=0.1 * r(nh * d),
-                 wo=torch.nn.Parameter(r(c, nh * d) * c ** -0.5), bo=0.1 * r(c), bias_table=r(13, 13))
+                 wo=torch.nn.Parameter(r(c, nh * d) * c ** -0.5), bo=0.1 * r(c), bias_table=r(2 * ws - 1, 2 * ws - 1))
+        call = lambda: ops.window_attention(x, y, num_heads=nh, head_dim=d, window_size=(ws, ws), shift=shift, ln_q=ln, ln_kv=ln,
+                                            residual=x, precision="bf16", **P)
+        with torch.no_grad():
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            reps = 5
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps + 2)]
+            e[0].record()
+            for _ in range(reps):
+                call()
+            e[1].record()
+            cold = []
+            for i in range(reps):
+                flush.fill_(i)
+                e[2 + 2 * i].record()
+                call()
+                e[3 + 2 * i].record()
+            torch.cuda.synchronize()
+            hot_us = e[0].elapsed_time(e[1]) / reps * 1e3
+            cold_us = sorted(e[2 + 2 * i].elapsed_time(e[3 + 2 * i]) for i in range(reps))[reps // 2] * 1e3
+        n_tok = b * side * side
+        t = ws * ws
+        flops = 8.0 * n_tok * c * c + 4.0 * t * n_tok * c
+        byts = 4.0 * n_tok * c * (3 if cross else 2)
+        t_tensor, t_hbm = flops / (PEAK_TF * 1e12) * 1e6, byts / (PEAK_GBS * 1e9) * 1e6
+        roof = max(t_tensor, t_hbm)
+        rows.append({"tag": tag, "window": ws, "heads": nh, "head_dim": d, "C": c, "B": b, "Hp": side, "tokens": n_tok, "shift": int(shift),
+                     "cross": int(cross), "us_l2_hot": round(hot_us, 1), "us_l2_flushed": round(cold_us, 1),
+                     "tflops": round(flops / hot_us / 1e6, 2), "pct_of_bf16_tensor_peak": round(100 * t_tensor / hot_us, 2),
+                     "hbm_gbs_ideal_fusion": round(byts / hot_us / 1e3, 1), "bound": "tensor" if t_tensor >= t_hbm else "hbm",
+                     "roof_us": round(roof, 1), "frac_of_roof": round(roof / hot_us, 4), "frac_of_roof_flushed": round(roof / cold_us, 4)})
+        del x, y
+
+    for (ws, nh, d, b, side) in MODEL_SHAPES:
         for cross in (False, True):
             for shift in (False, True):
-                call = lambda: ops.window_attention(x, y if cross else None, num_heads=nh, head_dim=d, window_size=(7, 7), shift=shift,
-                                                    ln_q=ln, ln_kv=ln, residual=x, precision="bf16", **P)
-                with torch.no_grad():
-                    for _ in range(2):
-                        call()          # warm-up: packs the weights once (cached on the parameter objects)
-                    torch.cuda.synchronize()
-                    ops.profile_enable(True)
-                    for _ in range(reps):
-                        call()
-                    torch.cuda.synchronize()
-                    prof = ops.profile_summary()
-                    ops.profile_enable(False)
-                n_tok = b * hp * hp
-                flops = 8.0 * n_tok * c * c + 196.0 * n_tok * c
-                kern = {k: round(v["total_ms"] / reps * 1e3, 1) for k, v in prof.items() if not k.startswith("pack")}
-                us = sum(kern.values())
-                core = [v for k, v in kern.items() if k.startswith("attn_core")]
-                rows.append({"C": c, "Hp": hp, "head_dim": d, "windows": b * (hp // 7) ** 2, "cross": cross, "shift": shift,
-                             "us_per_call": round(us, 1), "tflops": round(flops / us / 1e6, 2),
-                             "pct_of_bf16_tensor_peak": round(100 * flops / us / 1e6 / PEAK_TF, 2),
-                             "attn_core_us": core[0] if core else None, "kernels_us": kern})
-    print(json.dumps({"config": "BASELINE configs[4]: window attention microbench, B=64, 7x7 windows, 8 heads, bf16 path",
-                      "peak_tflops_sustained": PEAK_TF, "peak_hbm_gbs": PEAK_GBS, "rows": rows}, indent=1))
+                measure(ws, nh, d, b, side, shift, cross, "model")
+    windows = (7, 16) if args.quick else (7, 8, 14, 16)
+    heads = (8,) if args.quick else (4, 8, 16)
+    dims = (3, 32) if args.quick else (3, 6, 12, 24, 32, 48, 64)
+    tokens = (1 << 16,) if args.quick else (1 << 14, 1 << 18, 1 << 22)
+    for ws in windows:
+        for nh in heads:
+            for d in dims:
+                c = nh * d
+                if c % 4 or c > 384:
+                    skipped.append({"window": ws, "heads": nh, "head_dim": d, "why": "C %% 4 != 0 or C > 384 (tile limit of the tensor-core path)"})
+                    continue
+                for tk in tokens:
+                    if tk * c * 4 > (1 << 30):   # one fp32 map above 1 GiB: out of the sweep's memory budget
+                        continue
+                    b, side = geometry(ws, tk)
+                    for shift, cross in ((False, False), (True, True)):
+                        try:
+                            measure(ws, nh, d, b, side, shift, cross, "sweep")
+                        except Exception as ex:   # unsupported shape: reported, not hidden
+                            skipped.append({"window": ws, "heads": nh, "head_dim": d, "tokens": tk, "why": str(ex)[:160]})
+                            torch.cuda.synchronize()
+    print(json.dumps({"config": "BASELINE configs[4]: window attention microbench sweep, bf16 path, one operator call",
+                      "peak_tflops_sustained": PEAK_TF, "peak_hbm_gbs": PEAK_GBS, "rows": rows, "skipped": skipped}, indent=1))
 
 
 if __name__ == "__main__":
