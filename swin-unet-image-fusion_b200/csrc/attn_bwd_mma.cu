@@ -31,6 +31,7 @@ struct __align__(16) ItemSmem {
     uint32_t q[KC][64 * RSW], k[KC][64 * RSW], v[KC][64 * RSW], g[KC][64 * RSW];
     uint32_t qt[KC][16 * TSW], kt[KC][16 * TSW], gt[KC][16 * TSW], vt[KC][16 * TSW];
     float4 red[WARPS][14][32];      // per-warp partial dK^T / dV^T accumulator fragments
+    uint32_t tok2[2][64];           // token index (row of the un-shifted map) of every token of the window, same double buffering
     uint32_t rows2[2][64];          // element offset (token row * inner, < 2^32: checked by the launcher) of every token of the
                                     // window; double-buffered by item parity: the tail of item i reads them while item i+1 is set up
     int reg2[2][64];
@@ -58,6 +59,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// element offset inside a bf16 tensor in the UMMA-tiled layout [tile of 128 rows][8-column chunk][row][8]
+__device__ __forceinline__ uint32_t tiled_off(uint32_t t, uint32_t col, uint32_t nkc) {
+    return ((t >> 7) * nkc + (col >> 3)) * 1024u + (t & 127u) * 8u + (col & 7u);
 }
 __device__ __forceinline__ float quad_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -99,7 +104,8 @@ template <int D>
 __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                                                              const float* __restrict__ gO, float* __restrict__ dQ, float* __restrict__ dK,
                                                              float* __restrict__ dV, float* __restrict__ O, const float* __restrict__ table,
-                                                             float* __restrict__ gtable, WinGeom g, int inner, int nh, float scale, long long nitems) {
+                                                             float* __restrict__ gtable, WinGeom g, int inner, int nh, float scale, long long nitems,
+                                                             AttnBwdTiledOut to) {
     constexpr int NE = (T * D + WARPS * 32 - 1) / (WARPS * 32);
     constexpr int KC = (D + 15) / 16;     // 16-wide chunks of the head dimension
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -142,7 +148,9 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
         const int win = (int)(blockIdx.x / nh), head = (int)(blockIdx.x - (long long)win * nh);
         if (threadIdx.x < T) {
             int rg;
-            ws->rows2[0][threadIdx.x] = (uint32_t)(win_token_src(g, win, threadIdx.x, &rg) * inner);
+            const long long tk = win_token_src(g, win, threadIdx.x, &rg);
+            ws->tok2[0][threadIdx.x] = (uint32_t)tk;
+            ws->rows2[0][threadIdx.x] = (uint32_t)(tk * inner);
             ws->reg2[0][threadIdx.x] = rg;
         }
         __syncthreads();
@@ -156,6 +164,7 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
         const int win = (int)(item / nh), head = (int)(item - (long long)win * nh);
         const int hoff = head * D;
         const uint32_t* rows = ws->rows2[parity];
+        const uint32_t* tok = ws->tok2[parity];
         const int* reg = ws->reg2[parity];
         const long long nitem = item + gridDim.x;
         const int nwin = (int)(nitem / nh), nhead = (int)(nitem - (long long)nwin * nh);
@@ -173,7 +182,9 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
             store_flat<D, NE>(pc, reinterpret_cast<__half*>(ws->v[0]), reinterpret_cast<__half*>(ws->vt[0]), 1.f);
             if (nitem < nitems && threadIdx.x < T) {     // token rows of the next item (other parity: the previous item's tail is over)
                 int rg;
-                ws->rows2[parity ^ 1][threadIdx.x] = (uint32_t)(win_token_src(g, nwin, threadIdx.x, &rg) * inner);
+                const long long tk = win_token_src(g, nwin, threadIdx.x, &rg);
+                ws->tok2[parity ^ 1][threadIdx.x] = (uint32_t)tk;
+                ws->rows2[parity ^ 1][threadIdx.x] = (uint32_t)(tk * inner);
                 ws->reg2[parity ^ 1][threadIdx.x] = rg;
             }
             __syncthreads();
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
                 for (int nd = 0; nd < NDT_MAX; nd++) {
                     if (nd >= ndt) continue;
                     const int kr = (8 * nd + gq) * TSW + 8 * kk + tq;
-                    if (O) mma16816(o[nd], p0, p1, p2, p3, ws->vt[kc][kr], ws->vt[kc][kr + 4]);
+                    if (O || to.o) mma16816(o[nd], p0, p1, p2, p3, ws->vt[kc][kr], ws->vt[kc][kr + 4]);
                     mma16816(dq[nd], a0, a1, a2, a3, ws->kt[kc][kr], ws->kt[kc][kr + 4]);
                 }
             }
@@ -313,15 +324,26 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
                 for (int e = 0; e < 2; e++) {
                     const int dd = 16 * kc + 8 * nd + 2 * tq + e;
                     if (nd < ndt && dd < D) {
-                        if (r0 < T) {
-                            const uint32_t o0 = rows[r0] + (uint32_t)(hoff + dd);
-                            dQ[o0] = dq[nd][e] * f;
-                            if (O) O[o0] = o[nd][e];
-                        }
-                        if (r1 < T) {
-                            const uint32_t o1 = rows[r1] + (uint32_t)(hoff + dd);
-                            dQ[o1] = dq[nd][2 + e] * f;
-                            if (O) O[o1] = o[nd][2 + e];
+                        if (to.dqkv) {   // bf16, UMMA-tiled: the operands the projection GEMMs of the backward bulk-copy
+                            if (r0 < T) {
+                                to.dqkv[tiled_off(tok[r0], (uint32_t)(hoff + dd), to.nkc3)] = __float2bfloat16_rn(dq[nd][e] * f);
+                                to.o[tiled_off(tok[r0], (uint32_t)(hoff + dd), to.nkc1)] = __float2bfloat16_rn(o[nd][e]);
+                            }
+                            if (r1 < T) {
+                                to.dqkv[tiled_off(tok[r1], (uint32_t)(hoff + dd), to.nkc3)] = __float2bfloat16_rn(dq[nd][2 + e] * f);
+                                to.o[tiled_off(tok[r1], (uint32_t)(hoff + dd), to.nkc1)] = __float2bfloat16_rn(o[nd][2 + e]);
+                            }
+                        } else {
+                            if (r0 < T) {
+                                const uint32_t o0 = rows[r0] + (uint32_t)(hoff + dd);
+                                dQ[o0] = dq[nd][e] * f;
+                                if (O) O[o0] = o[nd][e];
+                            }
+                            if (r1 < T) {
+                                const uint32_t o1 = rows[r1] + (uint32_t)(hoff + dd);
+                                dQ[o1] = dq[nd][2 + e] * f;
+                                if (O) O[o1] = o[nd][2 + e];
+                            }
                         }
                     }
                 }
@@ -376,9 +398,15 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
                 for (int e = 0; e < 2; e++) {
                     const int key = 8 * n + 2 * tq + e;
                     if (key < T) {
-                        const uint32_t o = rows[key] + (uint32_t)hoff;
-                        if (d0 < D) dst[o + d0] = acc[e] * f;
-                        if (d0 + 8 < D) dst[o + d0 + 8] = acc[2 + e] * f;
+                        if (to.dqkv) {
+                            const uint32_t cb = (uint32_t)((isk ? to.inner : 2 * to.inner) + hoff);
+                            if (d0 < D) to.dqkv[tiled_off(tok[key], cb + (uint32_t)d0, to.nkc3)] = __float2bfloat16_rn(acc[e] * f);
+                            if (d0 + 8 < D) to.dqkv[tiled_off(tok[key], cb + (uint32_t)d0 + 8u, to.nkc3)] = __float2bfloat16_rn(acc[2 + e] * f);
+                        } else {
+                            const uint32_t o = rows[key] + (uint32_t)hoff;
+                            if (d0 < D) dst[o + d0] = acc[e] * f;
+                            if (d0 + 8 < D) dst[o + d0 + 8] = acc[2 + e] * f;
+                        }
                     }
                 }
             }
@@ -404,7 +432,7 @@ __global__ void __launch_bounds__(WARPS * 32, D <= 16 ? 3 : 2) k_attn_bwd_mma(co
 
 template <int D>
 int launch_one(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O, const float* table,
-               float* gtable, const WinGeom& g, int inner, int nh, long long nitems, cudaStream_t st) {
+               float* gtable, const WinGeom& g, int inner, int nh, long long nitems, cudaStream_t st, const AttnBwdTiledOut& to) {
     const size_t smem = sizeof(ItemSmem<(D + 15) / 16>);
     static DeviceOnce configured;
     if (configured.need()) {
@@ -414,7 +442,7 @@ int launch_one(const float* Q, const float* K, const float* V, const float* gO, 
     }
     long long grid = (long long)sm_count() * (D <= 16 ? 3 : 2);
     if (grid > nitems) grid = nitems;
-    k_attn_bwd_mma<D><<<(unsigned)grid, WARPS * 32, smem, st>>>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, 1.0f / sqrtf((float)D), nitems);
+    k_attn_bwd_mma<D><<<(unsigned)grid, WARPS * 32, smem, st>>>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, inner, nh, 1.0f / sqrtf((float)D), nitems, to);
     SF_CHECK_LAUNCH("bwd_attn_core_mma");
     return SF_OK;
 }
@@ -428,7 +456,15 @@ bool attn_core_bwd_mma_supported(const WinGeom& g, int d, int nh) {
 }
 
 int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV, float* O,
-                             const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st, int ld) {
+                             const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st, int ld,
+                             const AttnBwdTiledOut* tiled) {
+    AttnBwdTiledOut to{};
+    if (tiled) {
+        to = *tiled;
+        SF_CHECK_ARG(to.dqkv && to.o && to.inner == inner, "attention backward (mma): tiled outputs need both tensors");
+    } else {
+        SF_CHECK_ARG(dQ && dK && dV, "attention backward (mma): missing outputs");
+    }
     // ld: row stride (elements) shared by all eight tensors -- they may be column blocks of one [tokens x ld] buffer
     if (ld <= 0) ld = inner;
     SF_CHECK_ARG((long long)g.B * g.Hp * g.Wp * ld < (1LL << 32), "attention backward (mma): %d-wide rows exceed the 32-bit offset range", ld);
@@ -436,11 +472,11 @@ int launch_attn_core_bwd_mma(const float* Q, const float* K, const float* V, con
     const double mtok = (double)g.B * g.Hp * g.Wp;
     ProfScope ps(prof_name("bwd_attn_core_mma_d%d", d), (O ? 14.0 : 12.0) * g.T * mtok * inner, (O ? 32.0 : 28.0) * mtok * inner, st);
     switch (d) {
-        case 3: return launch_one<3>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
-        case 6: return launch_one<6>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
-        case 12: return launch_one<12>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
-        case 24: return launch_one<24>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
-        case 48: return launch_one<48>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st);
+        case 3: return launch_one<3>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st, to);
+        case 6: return launch_one<6>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st, to);
+        case 12: return launch_one<12>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st, to);
+        case 24: return launch_one<24>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st, to);
+        case 48: return launch_one<48>(Q, K, V, gO, dQ, dK, dV, O, table, gtable, g, ld, nh, nitems, st, to);
     }
     set_error("attention backward (mma): head_dim %d is not built", d);
     return SF_ERR_INVALID;

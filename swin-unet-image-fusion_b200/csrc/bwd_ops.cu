@@ -809,7 +809,7 @@ static WaBwdPlan wa_bwd_tc_plan(const sf_window_attn_params* p) {
     w.off_g = c.take(tiled_bytes(M, C));
     w.off_o = c.take(tiled_bytes(M, inner));
     w.off_dqkv = c.take(tiled_bytes(M, 3 * inner));
-    w.off_f32 = c.take(align_up((size_t)M * 8 * inner * sizeof(float)));
+    w.off_f32 = c.take(align_up((size_t)M * 4 * inner * sizeof(float)));
     w.off_gn = c.take(2 * align_up((size_t)M * C * sizeof(float)));
     w.total = c.off;
     return w;
@@ -819,7 +819,7 @@ static bool wa_bwd_tc_ok(const sf_window_attn_params* p) {
     const long long M = (long long)p->B * p->Hp * p->Wp;
     return bwd_tc_enabled() && p->C % 4 == 0 && (int)tc::pad16((uint32_t)p->C) <= TC_MAX_KPAD && inner % 8 == 0 &&
            (int)tc::pad16((uint32_t)inner) <= TC_MAX_KPAD && aligned16(p->q_src) && aligned16(p->kv_src) && M < 2147483647LL &&
-           M * 8 * inner < (1LL << 32);
+           M * 4 * inner < (1LL << 32);
 }
 static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, const float* gO, float* dQ, float* dK, float* dV,
                                 const float* table, float* gtable, const WinGeom& g, int inner, int nh, int d, cudaStream_t st, bool mma,
@@ -827,7 +827,7 @@ static int launch_attn_core_bwd(const float* Q, const float* K, const float* V, 
 static int window_attn_bwd_tc(const sf_window_attn_bwd_params* bp, void* ws_ptr, size_t ws_bytes, cudaStream_t st) {
     const sf_window_attn_params* p = &bp->fwd;
     const long long M = (long long)p->B * p->Hp * p->Wp;
-    const int C = p->C, inner = p->num_heads * p->head_dim, ld = 8 * inner;
+    const int C = p->C, inner = p->num_heads * p->head_dim, ld = 4 * inner;
     const WaBwdPlan w = wa_bwd_tc_plan(p);
     if (ws_bytes < w.total || !ws_ptr) { set_error("sf_window_attn_bwd: workspace too small (%zu B given, %zu needed)", ws_bytes, w.total); return SF_ERR_WORKSPACE; }
     char* base = reinterpret_cast<char*>(ws_ptr);
@@ -838,8 +838,7 @@ static int window_attn_bwd_tc(const sf_window_attn_bwd_params* bp, void* ws_ptr,
     bf16* o_t = reinterpret_cast<bf16*>(base + w.off_o);
     bf16* dqkv_t = reinterpret_cast<bf16*>(base + w.off_dqkv);
     float* F = reinterpret_cast<float*>(base + w.off_f32);
-    float *Q = F, *K = F + inner, *V = F + 2 * inner, *gO = F + 3 * inner, *O = F + 4 * inner, *dQ = F + 5 * inner, *dK = F + 6 * inner,
-          *dV = F + 7 * inner;
+    float *Q = F, *K = F + inner, *V = F + 2 * inner, *gO = F + 3 * inner;
     const size_t cs = align_up((size_t)M * C * sizeof(float));
     float* gnq = reinterpret_cast<float*>(base + w.off_gn);
     float* gnkv = reinterpret_cast<float*>(base + w.off_gn + cs);
@@ -893,15 +892,27 @@ static int window_attn_bwd_tc(const sf_window_attn_bwd_params* bp, void* ws_ptr,
         SF_TRY(launch_tc_gemm(t, "bwd_tc_dx_proj", st));
     }
     // ---- attention core (fp16 mma.sync adjoint; also delivers O = P V) ---------------------------------------------------------------
-    SF_TRY(launch_attn_core_bwd_mma(Q, K, V, gO, dQ, dK, dV, O, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads, p->head_dim, st, ld));
-    SF_TRY(launch_ln_to_tiled(O, nullptr, nullptr, o_t, M, inner, 0.f, st, nullptr, ld));
-    const int nkc3 = (int)tc::pad16((uint32_t)(3 * inner)) / 8;
-    if (3 * inner <= TC_MAX_KPAD) {
-        SF_TRY(launch_ln_to_tiled(dQ, nullptr, nullptr, dqkv_t, M, 3 * inner, 0.f, st, nullptr, ld));
-    } else {   // rows wider than one cast launch takes: three launches into the chunk ranges of the same tiled tensor
-        for (int s = 0; s < 3; s++)
-            SF_TRY(launch_ln_to_tiled(dQ + s * inner, nullptr, nullptr, dqkv_t, M, inner, 0.f, st, nullptr, ld, nkc3, s * (inner / 8)));
+    // its outputs (O = P V, dQ | dK | dV) leave as bf16 tiled tensors: the operands of the GEMMs below, no cast pass.
+    // Tail rows of the last tile and the padding columns are zeroed first (the weight-gradient GEMM sums over all rows).
+    const int nkc3 = (int)tc::pad16((uint32_t)(3 * inner)) / 8, nkc1 = (int)tc::pad16((uint32_t)inner) / 8;
+    {
+        const long long tiles = (M + 127) / 128;
+        const bool tail = (M & 127) != 0;
+        const bool padc = tc::pad16((uint32_t)inner) != (uint32_t)inner || tc::pad16((uint32_t)(3 * inner)) != (uint32_t)(3 * inner);
+        if (padc) {
+            if (cudaMemsetAsync(o_t, 0, tiled_bytes(M, inner), st) != cudaSuccess || cudaMemsetAsync(dqkv_t, 0, tiled_bytes(M, 3 * inner), st) != cudaSuccess) {
+                set_error("sf_window_attn_bwd: cudaMemsetAsync failed"); return SF_ERR_CUDA;
+            }
+        } else if (tail) {
+            if (cudaMemsetAsync(o_t + (size_t)(tiles - 1) * nkc1 * 1024, 0, (size_t)nkc1 * 2048, st) != cudaSuccess ||
+                cudaMemsetAsync(dqkv_t + (size_t)(tiles - 1) * nkc3 * 1024, 0, (size_t)nkc3 * 2048, st) != cudaSuccess) {
+                set_error("sf_window_attn_bwd: cudaMemsetAsync failed"); return SF_ERR_CUDA;
+            }
+        }
     }
+    AttnBwdTiledOut to{dqkv_t, o_t, (unsigned)nkc3, (unsigned)nkc1, inner};
+    SF_TRY(launch_attn_core_bwd_mma(Q, K, V, gO, nullptr, nullptr, nullptr, nullptr, p->bias_table, bp->g_bias_table, geom, inner, p->num_heads,
+                                    p->head_dim, st, ld, &to));
     // ---- weight gradients -------------------------------------------------------------------------------------------------------
     SF_TRY(launch_tc_wgrad(g_t, o_t, bp->g_wo, bp->g_bo, M, C, inner, "bwd_tc_wgrad", st));
     if (share) {

@@ -786,11 +786,41 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                 tc_fence_after_sync();
                 const uint32_t tlane = tmem_base + acc * acc_stride + ((uint32_t)(rb * 32) << 16);
                 const int ncol0 = c * p.NCH;
-                for (int c16 = eg * 16; c16 < p.NCH; c16 += 32) {
+                // 16-column groups of this warp: eg*16, eg*16 + 32, ...  Software pipeline: the TMEM load of group i+1 and the
+                // residual row segment of group i+1 (an L2 / HBM access, scattered in window order) are in flight while group i is
+                // converted and stored -- the serial form paid one memory latency per group (most of a wide projection's time).
+                int ngr = 0;
+                for (int c16 = eg * 16; c16 < p.NCH && ncol0 + c16 < p.N; c16 += 32) ngr++;
+                const bool res_vec = OUTMODE == OUT_F32 && p.residual && m < p.M && ((p.ldr & 3) == 0) && ((p.N & 3) == 0) &&
+                                     ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+                uint32_t rnext[16];
+                float4 rsn[4];
+                if (ngr > 0) {
+                    tmem_ld16_issue(tlane + (uint32_t)(eg * 16), rnext);
+                    if (res_vec) {
+                        const float* rp = p.residual + mo * p.ldr + ncol0 + eg * 16;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) rsn[i] = (ncol0 + eg * 16 + i * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(rp + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                for (int gi = 0; gi < ngr; gi++) {
+                    const int c16 = eg * 16 + 32 * gi;
                     const int n0 = ncol0 + c16;
-                    if (n0 >= p.N) break;  // uniform per warp
                     float v[16];
-                    tmem_ld16(tlane + (uint32_t)c16, v);
+                    float4 rsc[4];
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(rnext[i]);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) rsc[i] = rsn[i];
+                    if (gi + 1 < ngr) {
+                        tmem_ld16_issue(tlane + (uint32_t)(c16 + 32), rnext);
+                        if (res_vec) {
+                            const float* rp = p.residual + mo * p.ldr + n0 + 32;
+#pragma unroll
+                            for (int i = 0; i < 4; i++) rsn[i] = (n0 + 32 + i * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(rp + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
                     if (OUTMODE == OUT_TILED && m >= p.M && p.zero_tail) {
                         // rows past M of the last tile: zeros (the weight-gradient GEMM sums over the rows of this tensor)
                         bf16* o = reinterpret_cast<bf16*>(p.out);
@@ -860,7 +890,7 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                                 if (vec && n0 + i + 4 <= p.N) {
                                     float4 t = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                                     if (rs) {
-                                        float4 rr = *reinterpret_cast<const float4*>(rs + i);
+                                        const float4 rr = res_vec ? rsc[i >> 2] : *reinterpret_cast<const float4*>(rs + i);
                                         t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
                                     }
                                     *reinterpret_cast<float4*>(o + i) = t;
