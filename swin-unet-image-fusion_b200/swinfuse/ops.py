@@ -125,7 +125,8 @@ def y_crcb_to_rgb(fus_y: Tensor, crcb: Tensor) -> Tensor:
 # two kernels at a time.  Every dual operation is fully ordered at both ends, so tensors that cross
 # streams are never reused before their readers were ordered behind the join; the fork/join pattern is
 # also what CUDA-graph capture records as parallel branches.
-_dual_streams = True
+import os as _os
+_dual_streams = _os.environ.get("SWINFUSE_DUAL_STREAMS", "1") != "0"
 _side_streams = {}
 
 
