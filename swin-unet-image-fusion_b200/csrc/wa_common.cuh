@@ -5,6 +5,7 @@
 #include "bf16_kernels.cuh"
 #include "hmma_util.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace sf {
 using namespace tc;
@@ -138,13 +139,61 @@ __device__ __forceinline__ void wf_prefetch(uint8_t* raw, const float* __restric
     }
 }
 
+// ---- softmax without the row maximum ------------------------------------------------------------------------------------
+// Scores arrive in the log2 domain (q pre-scaled by d^-1/2 log2 e, bias x log2 e).  softmax is shift invariant, and
+// P = 2^s needs no shift at all while every row keeps its dominant terms inside the fp32 / bf16 exponent range: P and v are
+// bf16 MMA operands (same exponent range as fp32), the row sum l rides on the ones column of v in the fp32 accumulator.
+// A row whose l left [2^-100, 2^100] (|score| beyond ~100: overflow, inf, NaN, or everything flushed to zero) sends the
+// warp through the exact path once more: row maximum subtracted first (a001:343, torch softmax).  The fast path saves the
+// max tree, two shuffle rounds and one FADD per score, and it removes the longest dependency chain of the core.
+static constexpr float WF_L_MIN = 7.8886090522101181e-31f;   // 2^-100
+static constexpr float WF_L_MAX = 1.2676506002282294e30f;    // 2^100
+static constexpr float WF_MASKED = -1.4426950e10f;           // the reference overwrites masked scores with -1e10 (a001:310), log2 domain
+
+__device__ __forceinline__ void wf_apply_mask(float (&s)[7][4], uint32_t m0, uint32_t m1) {
+    if (m0 | m1) {
+#pragma unroll
+        for (int nt = 0; nt < 7; nt++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if ((m0 >> (2 * nt + e)) & 1u) s[nt][e] = WF_MASKED;
+                if ((m1 >> (2 * nt + e)) & 1u) s[nt][2 + e] = WF_MASKED;
+            }
+        }
+    }
+}
+// P = 2^(s - x) as bf16 A fragments; EXACT: x = row maxima (quad reduction), else x = 0 and no subtraction is emitted.
+// n-tile 6 holds keys 48..55: only key 48 (column 0, lanes tq == 0) is real; the padded ones carry bias -1e30 -> 2^s = 0
+template <bool EXACT>
+__device__ __forceinline__ void wf_softmax_p(const float (&s)[7][4], uint32_t (&pf)[7][2]) {
+    float x0 = 0.f, x1 = 0.f;
+    if (EXACT) {
+        x0 = fmaxf(s[0][0], s[0][1]); x1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+        for (int nt = 1; nt < 7; nt++) {
+            x0 = max3f(x0, s[nt][0], s[nt][1]);
+            x1 = max3f(x1, s[nt][2], s[nt][3]);
+        }
+        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 7; nt++) {
+        const float p0 = ex2f(EXACT ? s[nt][0] - x0 : s[nt][0]), p2 = ex2f(EXACT ? s[nt][2] - x1 : s[nt][2]);
+        const float p1 = nt < 6 ? ex2f(EXACT ? s[nt][1] - x0 : s[nt][1]) : 0.f, p3 = nt < 6 ? ex2f(EXACT ? s[nt][3] - x1 : s[nt][3]) : 0.f;
+        pf[nt][0] = pack_bf16x2(p0, p1);
+        pf[nt][1] = pack_bf16x2(p2, p3);
+    }
+}
+__device__ __forceinline__ bool wf_l_bad(float l) { return !(l > WF_L_MIN && l < WF_L_MAX); }
+
 // ---- phase D, d <= 3 (8-byte heads): four heads per warp pass (see k_attn_pack4 in attn_frag.cu) ------------------
 // warp = (slab, head parity par); lane (gq, tq) loads the 8 bytes of head hj = 2tq + par of its rows, so one set of
 // LDS covers four heads; head 2j + par lives in the k-slots fed by lanes tq == j (A fragment = lane select).
+// q, k rows are fp16, v rows bf16 (phase C).
 template <int PH, int HW>
 __device__ __forceinline__ void wf_attn_pack4(const __half* __restrict__ wbase, uint8_t* __restrict__ sA2, int rowbase,
                                               const float (&bias)[7][4], uint32_t m0, uint32_t m1, int d, int r0, int gq, int tq, int par) {
-    constexpr float MASKED = -1.4426950e10f;   // the reference overwrites masked scores with -1e10 (a001:310), log2 domain
     const int r1 = r0 + 8;
     const int hj = 2 * tq + par;
     const bool r0ok = r0 < WF_T, r1ok = r1 < WF_T;
@@ -169,50 +218,31 @@ __device__ __forceinline__ void wf_attn_pack4(const __half* __restrict__ wbase, 
     for (int j = 0; j < 4; j++) {
         const bool mine = tq == j;
         const uint32_t a0 = mine ? q[0].x : 0u, a1 = mine ? q[1].x : 0u, a2 = mine ? q[0].y : 0u, a3 = mine ? q[1].y : 0u;
-        float s[7][4];
-#pragma unroll
-        for (int nt = 0; nt < 7; nt++) mma16816_cd(s[nt], a0, a1, a2, a3, k[nt].x, k[nt].y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
-        if (m0 | m1) {
-#pragma unroll
-            for (int nt = 0; nt < 7; nt++) {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    if ((m0 >> (2 * nt + e)) & 1u) s[nt][e] = MASKED;
-                    if ((m1 >> (2 * nt + e)) & 1u) s[nt][2 + e] = MASKED;
-                }
-            }
-        }
-        float x0 = fmaxf(s[0][0], s[0][1]), x1 = fmaxf(s[0][2], s[0][3]);
-#pragma unroll
-        for (int nt = 1; nt < 7; nt++) {
-            x0 = max3f(x0, s[nt][0], s[nt][1]);
-            x1 = max3f(x1, s[nt][2], s[nt][3]);
-        }
-        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
-        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
-        uint32_t pf[7][2];
-#pragma unroll
-        for (int nt = 0; nt < 7; nt++) {
-            // n-tile 6 holds keys 48..55: only key 48 (column 0, lanes tq == 0) is real; the padded ones give ex2(-1e30) = 0
-            const float p0 = ex2f(s[nt][0] - x0), p2 = ex2f(s[nt][2] - x1);
-            const float p1 = nt < 6 ? ex2f(s[nt][1] - x0) : 0.f, p3 = nt < 6 ? ex2f(s[nt][3] - x1) : 0.f;
-            pf[nt][0] = pack_h2(p0, p1);
-            pf[nt][1] = pack_h2(p2, p3);
-        }
         float ox[4], oy[4];   // dims 0,1 / 2,3 of head 2*(col/2)+par; rows r0 | r1
-        mma16816_cd(ox, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][0], vt[1][0], 0.f, 0.f, 0.f, 0.f);
-        mma16816_cd(oy, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][1], vt[1][1], 0.f, 0.f, 0.f, 0.f);
+        float l0, l1;
+        auto pass = [&](auto exact) {
+            float s[7][4];
 #pragma unroll
-        for (int jj = 1; jj < 4; jj++) {
-            const uint32_t p0 = pf[2 * jj][0], p1 = pf[2 * jj][1];
-            const uint32_t p2 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][0] : 0u, p3 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][1] : 0u;
-            mma16816(ox, p0, p1, p2, p3, vt[2 * jj][0], (2 * jj + 1 < 7) ? vt[2 * jj + 1][0] : 0u);
-            mma16816(oy, p0, p1, p2, p3, vt[2 * jj][1], (2 * jj + 1 < 7) ? vt[2 * jj + 1][1] : 0u);
-        }
+            for (int nt = 0; nt < 7; nt++) mma16816_cd(s[nt], a0, a1, a2, a3, k[nt].x, k[nt].y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
+            wf_apply_mask(s, m0, m1);
+            uint32_t pf[7][2];
+            wf_softmax_p<decltype(exact)::value>(s, pf);
+            mma16816_bf16_z(ox, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][0], vt[1][0]);
+            mma16816_bf16_z(oy, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][1], vt[1][1]);
+#pragma unroll
+            for (int jj = 1; jj < 4; jj++) {
+                const uint32_t p0 = pf[2 * jj][0], p1 = pf[2 * jj][1];
+                const uint32_t p2 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][0] : 0u, p3 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][1] : 0u;
+                mma16816_bf16(ox, p0, p1, p2, p3, vt[2 * jj][0], (2 * jj + 1 < 7) ? vt[2 * jj + 1][0] : 0u);
+                mma16816_bf16(oy, p0, p1, p2, p3, vt[2 * jj][1], (2 * jj + 1 < 7) ? vt[2 * jj + 1][1] : 0u);
+            }
+            // softmax row sums = the ones column of v (dim d of every head: zero weights, bias 1); valid on the lanes tq == j
+            l0 = d == 3 ? oy[1] : (d == 2 ? oy[0] : ox[1]);
+            l1 = d == 3 ? oy[3] : (d == 2 ? oy[2] : ox[3]);
+        };
+        pass(std::false_type{});
+        if (__any_sync(0xffffffffu, mine && (wf_l_bad(l0) || wf_l_bad(l1)))) pass(std::true_type{});
         if (mine) {   // this lane's accumulator columns are its head: dims (ox[0],ox[1],oy[0],oy[1]) of row r0, [2],[3] of row r1
-            // softmax row sums = the ones column of v (dim d of every head: zero weights, bias 1)
-            const float l0 = d == 3 ? oy[1] : (d == 2 ? oy[0] : ox[1]);
-            const float l1 = d == 3 ? oy[3] : (d == 2 ? oy[2] : ox[3]);
             const float i0 = rcpf(l0), i1 = rcpf(l1);
             if (r0ok) *reinterpret_cast<uint2*>(o0) = make_uint2(pack_bf16x2(ox[0] * i0, ox[1] * i0), pack_bf16x2(oy[0] * i0, oy[1] * i0));
             if (r1ok) *reinterpret_cast<uint2*>(o0 + 128) = make_uint2(pack_bf16x2(ox[2] * i1, ox[3] * i1), pack_bf16x2(oy[2] * i1, oy[3] * i1));
@@ -226,7 +256,6 @@ template <int PH, int HW>
 __device__ __forceinline__ void wf_attn_dp8(const __half* __restrict__ wbase, uint8_t* __restrict__ sA2, int rowbase,
                                             const float (&bias)[7][4], uint32_t m0, uint32_t m1, int d, int r0, int gq, int tq, int sub,
                                             int lane) {
-    constexpr float MASKED = -1.4426950e10f;
     const int r1 = r0 + 8;
     const bool r0ok = r0 < WF_T, r1ok = r1 < WF_T;
     const int r0c = r0ok ? r0 : 48, r1c = r1ok ? r1 : r0c;
@@ -243,51 +272,36 @@ __device__ __forceinline__ void wf_attn_dp8(const __half* __restrict__ wbase, ui
         uint2 q0 = lds64(pq + uoff), q1 = lds64(pq + q1off + uoff);
         // k-slots 8..15 of the single k-step hold the NEXT head's columns: zero them on the Q side
         if (tq >= 2) { q0 = make_uint2(0u, 0u); q1 = make_uint2(0u, 0u); }
-        float s[7][4];
-#pragma unroll
-        for (int nt = 0; nt < 7; nt++) {
-            const uint2 kk = lds64(pk + (nt < 6 ? nt * 8 * PH : t6off) + uoff);
-            mma16816_cd(s[nt], q0.x, q1.x, q0.y, q1.y, kk.x, kk.y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
-        }
+        uint2 kk[7];
         uint32_t vb[7];
 #pragma unroll
-        for (int kt = 0; kt < 7; kt++) vb[kt] = movm_trans(lds32(pv + (kt < 6 ? kt * 8 * PH : t6off) + uoff));
-        if (m0 | m1) {
-#pragma unroll
-            for (int nt = 0; nt < 7; nt++) {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    if ((m0 >> (2 * nt + e)) & 1u) s[nt][e] = MASKED;
-                    if ((m1 >> (2 * nt + e)) & 1u) s[nt][2 + e] = MASKED;
-                }
-            }
-        }
-        float x0 = fmaxf(s[0][0], s[0][1]), x1 = fmaxf(s[0][2], s[0][3]);
-#pragma unroll
-        for (int nt = 1; nt < 7; nt++) {
-            x0 = max3f(x0, s[nt][0], s[nt][1]);
-            x1 = max3f(x1, s[nt][2], s[nt][3]);
-        }
-        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
-        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
-        uint32_t pf[7][2];
-#pragma unroll
         for (int nt = 0; nt < 7; nt++) {
-            const float p0 = ex2f(s[nt][0] - x0), p2 = ex2f(s[nt][2] - x1);
-            const float p1 = nt < 6 ? ex2f(s[nt][1] - x0) : 0.f, p3 = nt < 6 ? ex2f(s[nt][3] - x1) : 0.f;
-            pf[nt][0] = pack_h2(p0, p1);
-            pf[nt][1] = pack_h2(p2, p3);
+            kk[nt] = lds64(pk + (nt < 6 ? nt * 8 * PH : t6off) + uoff);
+            vb[nt] = movm_trans(lds32(pv + (nt < 6 ? nt * 8 * PH : t6off) + uoff));
         }
         float o[4];
-        mma16816_cd(o, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vb[0], vb[1], 0.f, 0.f, 0.f, 0.f);
+        float l0, l1;
+        auto pass = [&](auto exact) {
+            float s[7][4];
 #pragma unroll
-        for (int j = 1; j < 4; j++) {
-            const uint32_t a2 = (2 * j + 1 < 7) ? pf[2 * j + 1][0] : 0u, a3 = (2 * j + 1 < 7) ? pf[2 * j + 1][1] : 0u;
-            mma16816(o, pf[2 * j][0], pf[2 * j][1], a2, a3, vb[2 * j], (2 * j + 1 < 7) ? vb[2 * j + 1] : 0u);
-        }
-        // row sums = column d of P V (the ones column): quad lane (d % 8) / 2, element d % 2
-        const float c0 = (d & 1) ? o[1] : o[0], c1 = (d & 1) ? o[3] : o[2];
-        const float i0 = rcpf(__shfl_sync(0xffffffffu, c0, lsrc)), i1 = rcpf(__shfl_sync(0xffffffffu, c1, lsrc));
+            for (int nt = 0; nt < 7; nt++)
+                mma16816_cd(s[nt], q0.x, q1.x, q0.y, q1.y, kk[nt].x, kk[nt].y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
+            wf_apply_mask(s, m0, m1);
+            uint32_t pf[7][2];
+            wf_softmax_p<decltype(exact)::value>(s, pf);
+            mma16816_bf16_z(o, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vb[0], vb[1]);
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                const uint32_t a2 = (2 * j + 1 < 7) ? pf[2 * j + 1][0] : 0u, a3 = (2 * j + 1 < 7) ? pf[2 * j + 1][1] : 0u;
+                mma16816_bf16(o, pf[2 * j][0], pf[2 * j][1], a2, a3, vb[2 * j], (2 * j + 1 < 7) ? vb[2 * j + 1] : 0u);
+            }
+            // row sums = column d of P V (the ones column): quad lane (d % 8) / 2, element d % 2
+            const float c0 = (d & 1) ? o[1] : o[0], c1 = (d & 1) ? o[3] : o[2];
+            l0 = __shfl_sync(0xffffffffu, c0, lsrc); l1 = __shfl_sync(0xffffffffu, c1, lsrc);
+        };
+        pass(std::false_type{});
+        if (__any_sync(0xffffffffu, wf_l_bad(l0) || wf_l_bad(l1))) pass(std::true_type{});
+        const float i0 = rcpf(l0), i1 = rcpf(l1);
         uint8_t* o0 = sA2 + (uint32_t)head * WF_LBO + (uint32_t)(rowbase + r0) * 16u + (uint32_t)tq * 4u;
         if (r0ok) *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(o[0] * i0, o[1] * i0);
         if (r1ok) *reinterpret_cast<uint32_t*>(o0 + 128) = pack_bf16x2(o[2] * i1, o[3] * i1);

@@ -68,7 +68,7 @@ __device__ __forceinline__ void ws_helper_bar() { asm volatile("bar.sync 1, %0;"
 __device__ __forceinline__ void ws_attn_tok48(const __half* __restrict__ wbase, uint8_t* __restrict__ sA2, int rowbase,
                                               const float* __restrict__ sb48, bool mask_h, bool mask_w, int d, int gq, int tq, int lane) {
     constexpr int PH = WS_PH, HW = WS_HW;
-    constexpr float MASKED = -1.4426950e10f;
+    constexpr float MASKED = WF_MASKED;
     const uint2 q = lds64(wbase + 48 * PH + gq * 4);   // q of token 48, head gq (pre-scaled by d^-1/2 log2 e)
     const int t6row = gq == 0 ? 48 : gq;               // key tile 6: key 48 for its lane group, an existing row elsewhere (bias -1e30)
     float s[7][4];
@@ -107,7 +107,7 @@ __device__ __forceinline__ void ws_attn_tok48(const __half* __restrict__ wbase, 
     for (int nt = 0; nt < 7; nt++) {
         const float p0 = ex2f(s[nt][0] - x0);
         const float p1 = nt < 6 ? ex2f(s[nt][1] - x0) : 0.f;
-        pf[nt] = pack_h2(p0, p1);
+        pf[nt] = pack_bf16x2(p0, p1);   // v rows are bf16 (phase C)
     }
     // O[h][(h', dd)] = P[h] V: n-tile c holds heads 2c, 2c+1; V fragments are row-major loads transposed in registers
     float o[4][4];
@@ -121,7 +121,7 @@ __device__ __forceinline__ void ws_attn_tok48(const __half* __restrict__ wbase, 
             // key tile 6 (jj == 3, first half) holds key 48 only: the other lane groups read an existing row (their P is 0)
             const uint32_t b0 = movm_trans(lds32(wbase + (jj < 3 ? 2 * jj * 8 + gq : t6row) * PH + 2 * HW + 8 * c + 2 * tq));
             const uint32_t b1 = jj < 3 ? movm_trans(lds32(wbase + ((2 * jj + 1) * 8 + gq) * PH + 2 * HW + 8 * c + 2 * tq)) : 0u;
-            mma16816(o[c], a0, 0u, a2, 0u, b0, b1);
+            mma16816_bf16(o[c], a0, 0u, a2, 0u, b0, b1);
         }
     }
     // head gq lives in n-tile gq >> 1, columns 4 (gq & 1) .. + 3: lanes tq = 2 (gq & 1) (dims 0, 1) and + 1 (dims 2, 3)
@@ -291,8 +291,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
                 const int nrows = tile_rows(t);
                 mbar_wait_relaxed(&raw_full[slot], (uint32_t)(j / WS_RS) & 1u);
                 const uint8_t* raw = smem + L.raw + slot * L.raw_stride;
-                produce(smem + L.a1q[st], raw, p.ln_q_g, p.ln_q_b, nrows);
-                if (!self_attn) produce(smem + L.a1kv[st], raw + raw_kv, p.ln_kv_g, p.ln_kv_b, nrows);
+                if (!(p.debug & 2)) {
+                    produce(smem + L.a1q[st], raw, p.ln_q_g, p.ln_q_b, nrows);
+                    if (!self_attn) produce(smem + L.a1kv[st], raw + raw_kv, p.ln_kv_g, p.ln_kv_b, nrows);
+                }
                 fence_async_smem();
             }
             ws_helper_bar();   // A1 of tile j complete; every helper has finished iteration j - 1 (F(j-4) released its staging slot)
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
                 tc_fence_after_sync();
                 uint8_t* qrow = smem + L.qkv[st] + (uint32_t)row * PITCH;
 #pragma unroll
-                for (int half = 0; half < 2; half++) {   // three TMEM loads in flight per wait
+                for (int half = 0; half < ((p.debug & 4) ? 0 : 2); half++) {   // three TMEM loads in flight per wait
                     uint32_t r[3][16];
 #pragma unroll
                     for (int u = 0; u < 3; u++) tmem_ld16_issue(tlane + st * WS_D1_STRIDE + (uint32_t)(half * 48 + u * 16), r[u]);
@@ -352,8 +354,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
                                 v[i + 2] = __uint_as_float(r[u][i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[u][i + 3]) + bb.w;
                             }
                             uint4* dst = reinterpret_cast<uint4*>(qrow + c16 * 2);
-                            dst[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
-                            dst[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+                            if (c16 < 2 * HW) {   // q, k: fp16
+                                dst[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+                                dst[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+                            } else {              // v: bf16, the B operand of P V with P = 2^s (wf_softmax_p)
+                                dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                                dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                            }
                         }
                     }
                 }
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
             }
             __syncwarp();
             // ---- F(j-3): D2 + b_o + residual -> fp32 rows, scattered back (window reverse + un-shift as index math) --------------------
-            if (j >= 3 && j - 3 < J) {
+            if (j >= 3 && j - 3 < J && !(p.debug & 8)) {
                 const int jf = j - 3;
                 const uint32_t st = (uint32_t)jf & 1u, par = ((uint32_t)jf >> 1) & 1u;
                 const int t = tile_of(jf);
