@@ -82,6 +82,7 @@ struct TcGemm {
     // ---- tc_gemm_plan fills ----
     int a_tile_nkc, a_kc0;    // AM_TILED, optional: A is the chunk range [a_kc0, ..) of a tiled tensor with a_tile_nkc chunks per tile
     int Kpad, KS, n_slabs, a_nkc, NA, NS, n_groups, chunks_per_group;
+    int coal;                 // OUT_F32: rows leave through the shared-memory transposition (tc_gemm_plan sets it)
 };
 void tc_gemm_pick_nchunk(int Ntot, int* NCH, int* n_chunks);
 int tc_gemm_pick_ks(int Kpad);          // k-slab width: largest of {64,48,32,16} dividing Kpad

@@ -9,6 +9,13 @@
 #include "tc_common.cuh"
 
 namespace sf {
+
+// rows at least this wide are normalised by the LayerNorm pre-pass (k_ln_to_tiled) instead of the GEMM's own producers
+static int ln_prepass_min_c() {
+    static const int v = [] { const char* e = getenv("SWINFUSE_LN_PREPASS_MIN_C"); return e ? atoi(e) : TC_LN_PREPASS_MIN_C; }();
+    return v;
+}
+
 using namespace tc;
 
 // =============================================================================================
@@ -52,8 +59,8 @@ static WaPlan wa_plan(const sf_window_attn_params* p) {
     w.off_qkv = c.take(w.fused ? 0 : tiled_elems(M, 3 * ocols) * sizeof(bf16));   // fp16 rows
     w.off_o = c.take(w.fused ? 0 : tiled_elems(M, ocols) * sizeof(bf16));
     w.off_packed = c.take(p->packed ? 0 : w.packed_bytes);
-    w.prepass_q = p->ln_q_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
-    w.prepass_kv = !w.self_attn && p->ln_kv_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
+    w.prepass_q = p->ln_q_gamma != nullptr && p->C >= ln_prepass_min_c();
+    w.prepass_kv = !w.self_attn && p->ln_kv_gamma != nullptr && p->C >= ln_prepass_min_c();
     w.off_nq = c.take(w.prepass_q ? tiled_elems(M, p->C) * sizeof(bf16) : 0);
     w.off_nkv = c.take(w.prepass_kv ? tiled_elems(M, p->C) * sizeof(bf16) : 0);
     w.total = c.off;
@@ -202,7 +209,7 @@ static MlpPlan mlp_plan(const sf_mlp_params* p) {
     Carver c;
     m.off_h = c.take(tiled_elems(p->M, p->hidden) * sizeof(bf16));
     m.off_packed = c.take(p->packed ? 0 : m.packed_bytes);
-    m.prepass = p->ln_gamma != nullptr && p->C >= TC_LN_PREPASS_MIN_C;
+    m.prepass = p->ln_gamma != nullptr && p->C >= ln_prepass_min_c();
     m.off_n = c.take(m.prepass ? tiled_elems(p->M, p->C) * sizeof(bf16) : 0);
     m.total = c.off;
     return m;

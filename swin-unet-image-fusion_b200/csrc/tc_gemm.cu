@@ -31,6 +31,8 @@ static constexpr uint32_t SBO = 128;
 static constexpr int G_THREADS = 576;          // RESIDENT flavour: 8 producer + MMA + loader + 8 epilogue warps
 static constexpr int G_THREADS_STREAM = 320;   // STREAM flavour: no producer warps
 static constexpr size_t SMEM_LIMIT = 227 * 1024;
+static constexpr uint32_t EPI_TR_PITCH = 20;                           // floats per staged row: 16 columns + 4 (bank spread)
+static constexpr uint32_t EPI_TR_BYTES = 32 * EPI_TR_PITCH * 4;        // one epilogue warp: 32 rows x 16 columns
 
 __host__ __device__ static inline uint32_t align128(uint32_t v) { return (v + 127) & ~127u; }
 
@@ -696,7 +698,7 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
 // the kernel
 // =============================================================================================
 struct GemmSmem {
-    uint32_t a_bytes, a_off[2], w_off, stage_bytes, slabA_bytes, slabW_bytes, bias_off, bar_off, total;
+    uint32_t a_bytes, a_off[2], w_off, stage_bytes, slabA_bytes, slabW_bytes, bias_off, tr_off, bar_off, total;
 };
 
 __host__ __device__ static inline GemmSmem gemm_smem_layout(const TcGemm& p) {
@@ -710,7 +712,8 @@ __host__ __device__ static inline GemmSmem gemm_smem_layout(const TcGemm& p) {
     s.slabA_bytes = stream ? (uint32_t)(p.KS >> 3) * LBO_T : 0u;
     s.stage_bytes = align128(s.slabW_bytes) + align128(s.slabA_bytes);
     s.bias_off = s.w_off + (uint32_t)p.NS * s.stage_bytes;
-    s.bar_off = s.bias_off + align128(p.bias ? (uint32_t)p.n_chunks * (uint32_t)p.NCH * 4u : 0u);
+    s.tr_off = s.bias_off + align128(p.bias ? (uint32_t)p.n_chunks * (uint32_t)p.NCH * 4u : 0u);
+    s.bar_off = s.tr_off + ((p.out_mode == OUT_F32 && p.coal) ? 8u * EPI_TR_BYTES : 0u);   // fp32 rows leave through a per-warp transposition buffer
     s.total = s.bar_off + 256;
     return s;
 }
@@ -877,6 +880,21 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
             if (OUTMODE == OUT_F32 && p.win_order && m < p.M) mo = win_order_token(p.wo, (uint32_t)m);
             const int c0 = group * p.chunks_per_group;
             const int c1 = min(c0 + p.chunks_per_group, p.n_chunks);
+            // fp32 rows, coalesced (p.coal): a thread owns a ROW of the accumulator (TMEM lane), so storing its 64-byte segment directly
+            // makes every warp instruction touch 32 lines.  The 32 x 16 block goes through shared memory instead and leaves as 8 rows x
+            // 64 contiguous bytes per instruction (lane l: rows 8k + l/4, float4 l%4); the residual arrives in the same mapping.
+            const bool coal = OUTMODE == OUT_F32 && STREAM && p.coal;   // the producer flavours (576 threads, 96 registers) keep direct stores
+            long long mo4[4];
+            bool ok4[4];
+            if (OUTMODE == OUT_F32 && STREAM && coal) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int src = 8 * k + (lane >> 2);
+                    mo4[k] = __shfl_sync(0xffffffffu, mo, src);
+                    ok4[k] = tile * 128 + rb * 32 + src < p.M;
+                }
+            }
+            float* trbuf = reinterpret_cast<float*>(smem + L.tr_off + (uint32_t)(warp - (PW + 2)) * EPI_TR_BYTES);
             for (int c = c0; c < c1; c++, tcount++) {
                 const uint32_t acc = tcount & 1u;
                 mbar_wait_relaxed(&d_full[acc], (tcount >> 1) & 1u);
@@ -895,7 +913,13 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                 float4 rsn[4];
                 if (ngr > 0) {
                     tmem_ld16_issue(tlane + (uint32_t)(eg * 16), rnext);
-                    if (res_vec) {
+                    if (OUTMODE == OUT_F32 && STREAM && coal) {
+                        if (p.residual) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                rsn[k] = ok4[k] ? *reinterpret_cast<const float4*>(p.residual + mo4[k] * p.ldr + ncol0 + eg * 16 + (lane & 3) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    } else if (res_vec) {
                         const float* rp = p.residual + mo * p.ldr + ncol0 + eg * 16;
 #pragma unroll
                         for (int i = 0; i < 4; i++) rsn[i] = (ncol0 + eg * 16 + i * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(rp + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -913,11 +937,44 @@ __global__ void __launch_bounds__(AMODE == AM_TILED ? G_THREADS_STREAM : G_THREA
                     for (int i = 0; i < 4; i++) rsc[i] = rsn[i];
                     if (gi + 1 < ngr) {
                         tmem_ld16_issue(tlane + (uint32_t)(c16 + 32), rnext);
-                        if (res_vec) {
+                        if (OUTMODE == OUT_F32 && STREAM && coal) {
+                            if (p.residual) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++)
+                                    rsn[k] = ok4[k] ? *reinterpret_cast<const float4*>(p.residual + mo4[k] * p.ldr + n0 + 32 + (lane & 3) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        } else if (res_vec) {
                             const float* rp = p.residual + mo * p.ldr + n0 + 32;
 #pragma unroll
                             for (int i = 0; i < 4; i++) rsn[i] = (n0 + 32 + i * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(rp + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
+                    }
+                    if (OUTMODE == OUT_F32 && STREAM && coal) {
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(sbias + n0 + i);
+                                v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+                            }
+                        }
+                        if (p.elu) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) v[i] = elu_fast(v[i]);
+                        }
+                        float4* mine = reinterpret_cast<float4*>(trbuf + (uint32_t)lane * EPI_TR_PITCH);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) mine[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            float4 t = *reinterpret_cast<const float4*>(trbuf + (uint32_t)(8 * k + (lane >> 2)) * EPI_TR_PITCH + (uint32_t)(lane & 3) * 4u);
+                            if (ok4[k]) {
+                                if (p.residual) { t.x += rsc[k].x; t.y += rsc[k].y; t.z += rsc[k].z; t.w += rsc[k].w; }
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mo4[k] * p.ldo + p.out_col0 + n0 + (lane & 3) * 4) = t;
+                            }
+                        }
+                        __syncwarp();   // the block is read before the next group overwrites it
+                        continue;
                     }
                     if (OUTMODE == OUT_TILED && m >= p.M && p.zero_tail) {
                         // rows past M of the last tile: zeros (the weight-gradient GEMM sums over the rows of this tensor)
@@ -1044,6 +1101,11 @@ int tc_gemm_plan(TcGemm* p) {
         if (p->a_tile_nkc <= 0) { p->a_tile_nkc = p->a_nkc; p->a_kc0 = 0; }   // else: A is a column range of a wider tiled tensor
     }
     SF_CHECK_ARG(!p->win_order || p->M < 2147483647LL, "tc_gemm: %lld rows exceed the window-order index range", p->M);
+    {   // fp32 rows through the shared-memory transposition when every access can be a float4 (SWINFUSE_GEMM_COAL=0: direct stores)
+        static const bool coal_on = [] { const char* e = getenv("SWINFUSE_GEMM_COAL"); return !(e && e[0] == '0'); }();
+        p->coal = (coal_on && p->out_mode == OUT_F32 && p->a_mode == AM_TILED && (p->N & 15) == 0 && (p->ldo & 3) == 0 && (p->out_col0 & 3) == 0 && aligned16(p->out) &&
+                   (!p->residual || ((p->ldr & 3) == 0 && aligned16(p->residual)))) ? 1 : 0;
+    }
     const long long m_tiles = (p->M + 127) / 128;
     // spread the n-chunks of one m-tile over several CTAs only when there are too few m-tiles
     int groups = 1;
