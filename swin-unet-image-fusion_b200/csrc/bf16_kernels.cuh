@@ -139,6 +139,7 @@ struct TcMlp {
     const float* b1;   // [Hpad] zero padded
     const float* b2;   // [Cpad] zero padded
     int max_stages;    // depth cap of the raw-tile ring (<= 8)
+    int bulk_out;      // output rows are completed in place in the ring slot and leave by bulk copy (set by launch_tc_mlp)
 };
 bool tc_mlp_supported(int C, int hidden);
 int launch_tc_mlp(const TcMlp& t, cudaStream_t st);

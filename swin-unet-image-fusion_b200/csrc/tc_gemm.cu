@@ -508,93 +508,6 @@ __global__ void __launch_bounds__(256) k_ln_to_tiled(const float* __restrict__ i
     }
 }
 
-// Wide rows, coalesced stores: a CTA normalises LT_ROWS consecutive rows into a shared-memory image of its part of the
-// tiled tensor ([k-chunk][row][8 bf16], k-chunk pitch padded by 16 bytes so that the 8-byte fragment stores of a warp spread
-// over the banks) and the bulk-copy engine writes it out: one cp.async.bulk per k-chunk, LT_ROWS * 16 contiguous bytes each.
-// k_ln_to_tiled above stores 8-byte fragments 2 KB apart (half-filled sectors): 2.0 - 2.7 TB/s; this one writes whole lines.
-static constexpr int LT_ROWS = 32;
-static constexpr uint32_t LT_PITCH = LT_ROWS * 16 + 16;
-template <int LPR>
-__global__ void __launch_bounds__(256) k_ln_to_tiled_bulk(const float* __restrict__ in, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, bf16* __restrict__ out, long long M, int C, int Kpad,
-                                                          float eps, int gather, WinOrder wo, long long ld_in, int out_nkc, int out_kc0) {
-    extern __shared__ __align__(128) uint8_t lt_smem[];
-    constexpr int RPW = 32 / LPR;               // rows a warp handles at once
-    constexpr int ITER = LT_ROWS / (8 * RPW);   // row groups per warp: all of their loads are issued before the first reduction
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l = lane & (LPR - 1), sub = lane / LPR;
-    const int nf4 = C >> 2, nslots = Kpad >> 2, nkc = Kpad >> 3;
-    const long long row0 = (long long)blockIdx.x * LT_ROWS;   // the grid covers the rows up to the end of the last 128-row tile
-    float4 v[ITER][3];
-#pragma unroll
-    for (int it = 0; it < ITER; it++) {
-        const long long row = row0 + (warp + 8 * it) * RPW + sub;
-        const bool real = row < M;
-        const long long srow = (gather && real) ? win_order_token(wo, (uint32_t)row) : row;
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int q = l + LPR * i;
-            v[it][i] = (real && q < nf4) ? *reinterpret_cast<const float4*>(in + srow * ld_in + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < ITER; it++) {
-        const int rl = (warp + 8 * it) * RPW + sub;
-        const bool real = row0 + rl < M;
-        float mean = 0.f, rstd = 1.f;
-        if (gamma) {
-            float sm = 0.f;
-#pragma unroll
-            for (int i = 0; i < 3; i++) sm += (v[it][i].x + v[it][i].y) + (v[it][i].z + v[it][i].w);
-#pragma unroll
-            for (int o = LPR >> 1; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-            mean = sm / (float)C;   // the same arithmetic as k_ln_to_tiled: bit-identical tiles
-            float ss = 0.f;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                if (l + LPR * i < nf4) {
-                    const float dx = v[it][i].x - mean, dy = v[it][i].y - mean, dz = v[it][i].z - mean, dw = v[it][i].w - mean;
-                    ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-                }
-            }
-#pragma unroll
-            for (int o = LPR >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            rstd = rsqrtf(ss / (float)C + eps);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int q = l + LPR * i;
-            if (q < nslots) {
-                uint2 pk = make_uint2(0u, 0u);   // rows past M and the K padding are zeros (the weight-gradient GEMM sums over token rows)
-                if (real && q < nf4) {
-                    const float4 x = v[it][i];
-                    if (gamma) {
-                        const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + q), bb = __ldg(reinterpret_cast<const float4*>(beta) + q);
-                        pk = make_uint2(pack_bf16x2((x.x - mean) * rstd * gg.x + bb.x, (x.y - mean) * rstd * gg.y + bb.y),
-                                        pack_bf16x2((x.z - mean) * rstd * gg.z + bb.z, (x.w - mean) * rstd * gg.w + bb.w));
-                    } else {
-                        pk = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-                    }
-                }
-                *reinterpret_cast<uint2*>(lt_smem + (uint32_t)(q >> 1) * LT_PITCH + (uint32_t)rl * 16u + (uint32_t)(q & 1) * 8u) = pk;
-            }
-        }
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (warp == 0) {
-        const long long tile = row0 >> 7;
-        const int r = (int)(row0 & 127);
-        for (int kc = lane; kc < nkc; kc += 32) {
-            bf16* dst = out + ((tile * out_nkc + out_kc0 + kc) * 128 + r) * 8;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(lt_smem + (uint32_t)kc * LT_PITCH)),
-                         "n"(LT_ROWS * 16)
-                         : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the image must outlive the copies' reads
-    }
-}
-
 // Narrow rows (Kpad <= 64): one thread per row -- a warp-per-row mapping would leave most lanes idle at C = 24 / 48.
 // A warp reads 32 consecutive rows (one contiguous span, completed out of L1 over the NF4 loads) and stores
 // 32 consecutive 16-byte chunks per k-chunk.
@@ -671,16 +584,10 @@ int launch_ln_to_tiled(const float* in, const float* gamma, const float* beta, b
         return SF_OK;
     }
     const WinOrder woa = wo ? *wo : WinOrder{};
-    static const bool legacy = [] { const char* e = getenv("SWINFUSE_LN_TILED_BULK"); return e && e[0] == '0'; }();
-    if (!legacy) {
-        const long long nb = (M + 127) / 128 * (128 / LT_ROWS);
-        const size_t sh = (size_t)(Kpad >> 3) * LT_PITCH;
-        if (Kpad <= 96) k_ln_to_tiled_bulk<8><<<(unsigned)nb, 256, sh, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa, ld_in, out_nkc, out_kc0);
-        else if (Kpad <= 192) k_ln_to_tiled_bulk<16><<<(unsigned)nb, 256, sh, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa, ld_in, out_nkc, out_kc0);
-        else k_ln_to_tiled_bulk<32><<<(unsigned)nb, 256, sh, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa, ld_in, out_nkc, out_kc0);
-        SF_CHECK_LAUNCH("ln_to_tiled");
-        return SF_OK;
-    }
+    // (Round 2 tried a variant that builds the tile image in shared memory and writes it out with cp.async.bulk, whole lines instead
+    // of 8-byte fragments 2 KB apart: bit-identical output, same device time within 0.1 % in a same-box A/B -- a 12 us kernel moving
+    // 29 MB is launch ramp and DRAM page opening, not store efficiency.  Removed.  Likewise requesting the first k-slabs before the
+    // GEMM's prologue barrier: +1 % step time, removed.)
     if (Kpad <= 96) {
         blocks = std::min<long long>((M / 4 * 32 + 255) / 256 + 1, (long long)sm_count() * 16);
         k_ln_to_tiled<8><<<(unsigned)blocks, 256, 0, st>>>(in, gamma, beta, out, M, C, Kpad, eps, wo ? 1 : 0, woa, ld_in, out_nkc, out_kc0);

@@ -18,6 +18,7 @@
 // the producers run one tile ahead, GEMM1 of tile t+1 overlaps the ELU stage of tile t, and GEMM2 of
 // tile t overlaps the output stage of tile t-1.
 #include <type_traits>
+#include <cstdlib>
 #include "bf16_kernels.cuh"
 #include "tc_common.cuh"
 
@@ -298,6 +299,45 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_tc_mlp(TcMlp p) {
             __syncwarp();
             tc_fence_after_sync();
             const uint32_t tlane = tmem_base + 2u * d1_stride + b * d2_stride + ((uint32_t)(rb * 32) << 16);
+            if (ring_res && p.bulk_out) {
+                // The tile's rows are contiguous in HBM: each row is completed IN PLACE in its ring slot (x + MLP(x)) and the warp's 32
+                // rows leave as one bulk copy -- no thread-per-row stores (32 lines per instruction at a 4C-byte pitch).
+                float4* slot = reinterpret_cast<float4*>(smem + L.ring + (uint32_t)(t % NS) * L.tile_bytes + (size_t)row * p.C * 4);
+#pragma unroll
+                for (int g16 = 0; g16 < 4; g16++) {
+                    const int c16 = g16 * 16;
+                    if (c16 < p.C) {   // uniform
+                        float v[16];
+                        tmem_ld16(tlane + (uint32_t)c16, v);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            if (c16 + i + 4 <= p.C) {
+                                const float4 bb = *reinterpret_cast<const float4*>(sb2 + c16 + i);
+                                const float4 q4 = rr[g16 * 4 + (i >> 2)];
+                                slot[(c16 + i) >> 2] = make_float4(v[i] + bb.x + q4.x, v[i + 1] + bb.y + q4.y, v[i + 2] + bb.z + q4.z, v[i + 3] + bb.w + q4.w);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive1(&d2_empty[b]);
+                    const long long r0 = tile * 128 + rb * 32;
+                    const long long nrow = p.M - r0 < 32 ? p.M - r0 : 32;
+                    if (nrow > 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + r0 * p.C),
+                                     "r"(smem_u32(smem + L.ring + (uint32_t)(t % NS) * L.tile_bytes + (uint32_t)(rb * 32) * (uint32_t)p.C * 4u)),
+                                     "r"((uint32_t)nrow * (uint32_t)p.C * 4u)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the slot is refilled once its rows have been read
+                    }
+                    mbar_arrive1(&x_empty[(uint32_t)(t % NS)]);
+                }
+                continue;
+            }
 #pragma unroll
             for (int g16 = 0; g16 < 4; g16++) {
                 const int c16 = g16 * 16;
@@ -340,7 +380,12 @@ bool tc_mlp_supported(int C, int hidden) {
     return cols <= 512 && L.nstage >= 2 && L.total <= M_SMEM_LIMIT;
 }
 
-int launch_tc_mlp(const TcMlp& t, cudaStream_t st) {
+int launch_tc_mlp(const TcMlp& t_in, cudaStream_t st) {
+    TcMlp t = t_in;
+    {
+        static const bool bulk = [] { const char* e = getenv("SWINFUSE_MLP_BULK_OUT"); return !(e && e[0] == '0'); }();
+        t.bulk_out = (bulk && ((reinterpret_cast<uintptr_t>(t.out) & 15) == 0)) ? 1 : 0;
+    }
     SF_CHECK_ARG(tc_mlp_supported(t.C, t.hidden), "tc_mlp: unsupported shape C=%d hidden=%d", t.C, t.hidden);
     const MlpSmem L = mlp_smem_layout(t.Cpad, t.Hpad, t.Cpad, t.C, t.max_stages);
     static DeviceOnce configured;
