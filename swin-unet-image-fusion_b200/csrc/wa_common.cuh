@@ -214,40 +214,81 @@ __device__ __forceinline__ void wf_attn_pack4(const __half* __restrict__ wbase, 
         vt[nt][1] = movm_trans(vr.y);
     }
     uint8_t* o0 = sA2 + (uint32_t)(hj >> 1) * WF_LBO + (uint32_t)(rowbase + r0) * 16u + (uint32_t)(hj & 1) * 8u;
+    // One pass over the four heads.  The fast pass (EXACT = false) is straight-line code: key tiles stream through
+    // QK^T -> 2^s -> P V two at a time (no row maximum means no dependency between key tiles), so the scheduler overlaps the
+    // MUFU work of one head with the tensor-core work of the next; the row-sum check is one vote per task.
+    auto pass = [&](auto exact) -> bool {
+        constexpr bool EXACT = decltype(exact)::value;
+        bool bad = false;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const bool mine = tq == j;
-        const uint32_t a0 = mine ? q[0].x : 0u, a1 = mine ? q[1].x : 0u, a2 = mine ? q[0].y : 0u, a3 = mine ? q[1].y : 0u;
-        float ox[4], oy[4];   // dims 0,1 / 2,3 of head 2*(col/2)+par; rows r0 | r1
-        float l0, l1;
-        auto pass = [&](auto exact) {
-            float s[7][4];
+        for (int j = 0; j < 4; j++) {
+            const bool mine = tq == j;
+            const uint32_t a0 = mine ? q[0].x : 0u, a1 = mine ? q[1].x : 0u, a2 = mine ? q[0].y : 0u, a3 = mine ? q[1].y : 0u;
+            float ox[4], oy[4];   // dims 0,1 / 2,3 of head 2*(col/2)+par; rows r0 | r1
+            if (EXACT) {
+                float s[7][4];
 #pragma unroll
-            for (int nt = 0; nt < 7; nt++) mma16816_cd(s[nt], a0, a1, a2, a3, k[nt].x, k[nt].y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
-            wf_apply_mask(s, m0, m1);
-            uint32_t pf[7][2];
-            wf_softmax_p<decltype(exact)::value>(s, pf);
-            mma16816_bf16_z(ox, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][0], vt[1][0]);
-            mma16816_bf16_z(oy, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][1], vt[1][1]);
+                for (int nt = 0; nt < 7; nt++) mma16816_cd(s[nt], a0, a1, a2, a3, k[nt].x, k[nt].y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
+                wf_apply_mask(s, m0, m1);
+                uint32_t pf[7][2];
+                wf_softmax_p<true>(s, pf);
+                mma16816_bf16_z(ox, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][0], vt[1][0]);
+                mma16816_bf16_z(oy, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vt[0][1], vt[1][1]);
 #pragma unroll
-            for (int jj = 1; jj < 4; jj++) {
-                const uint32_t p0 = pf[2 * jj][0], p1 = pf[2 * jj][1];
-                const uint32_t p2 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][0] : 0u, p3 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][1] : 0u;
-                mma16816_bf16(ox, p0, p1, p2, p3, vt[2 * jj][0], (2 * jj + 1 < 7) ? vt[2 * jj + 1][0] : 0u);
-                mma16816_bf16(oy, p0, p1, p2, p3, vt[2 * jj][1], (2 * jj + 1 < 7) ? vt[2 * jj + 1][1] : 0u);
+                for (int jj = 1; jj < 4; jj++) {
+                    const uint32_t p0 = pf[2 * jj][0], p1 = pf[2 * jj][1];
+                    const uint32_t p2 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][0] : 0u, p3 = (2 * jj + 1 < 7) ? pf[2 * jj + 1][1] : 0u;
+                    mma16816_bf16(ox, p0, p1, p2, p3, vt[2 * jj][0], (2 * jj + 1 < 7) ? vt[2 * jj + 1][0] : 0u);
+                    mma16816_bf16(oy, p0, p1, p2, p3, vt[2 * jj][1], (2 * jj + 1 < 7) ? vt[2 * jj + 1][1] : 0u);
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {   // k-step jj of P V = key tiles 2jj, 2jj + 1
+                    uint32_t pf[2][2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int nt = 2 * jj + h;
+                        if (nt < 7) {
+                            float s[4];
+                            mma16816_cd(s, a0, a1, a2, a3, k[nt].x, k[nt].y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
+                            if (m0 | m1) {
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    if ((m0 >> (2 * nt + e)) & 1u) s[e] = WF_MASKED;
+                                    if ((m1 >> (2 * nt + e)) & 1u) s[2 + e] = WF_MASKED;
+                                }
+                            }
+                            // n-tile 6 holds keys 48..55: only key 48 (column 0, lanes tq == 0) is real; the others carry bias -1e30
+                            pf[h][0] = pack_bf16x2(ex2f(s[0]), nt < 6 ? ex2f(s[1]) : 0.f);
+                            pf[h][1] = pack_bf16x2(ex2f(s[2]), nt < 6 ? ex2f(s[3]) : 0.f);
+                        } else {
+                            pf[h][0] = 0u; pf[h][1] = 0u;
+                        }
+                    }
+                    const uint32_t b0x = vt[2 * jj][0], b0y = vt[2 * jj][1];
+                    const uint32_t b1x = (2 * jj + 1 < 7) ? vt[2 * jj + 1][0] : 0u, b1y = (2 * jj + 1 < 7) ? vt[2 * jj + 1][1] : 0u;
+                    if (jj == 0) {
+                        mma16816_bf16_z(ox, pf[0][0], pf[0][1], pf[1][0], pf[1][1], b0x, b1x);
+                        mma16816_bf16_z(oy, pf[0][0], pf[0][1], pf[1][0], pf[1][1], b0y, b1y);
+                    } else {
+                        mma16816_bf16(ox, pf[0][0], pf[0][1], pf[1][0], pf[1][1], b0x, b1x);
+                        mma16816_bf16(oy, pf[0][0], pf[0][1], pf[1][0], pf[1][1], b0y, b1y);
+                    }
+                }
             }
             // softmax row sums = the ones column of v (dim d of every head: zero weights, bias 1); valid on the lanes tq == j
-            l0 = d == 3 ? oy[1] : (d == 2 ? oy[0] : ox[1]);
-            l1 = d == 3 ? oy[3] : (d == 2 ? oy[2] : ox[3]);
-        };
-        pass(std::false_type{});
-        if (__any_sync(0xffffffffu, mine && (wf_l_bad(l0) || wf_l_bad(l1)))) pass(std::true_type{});
-        if (mine) {   // this lane's accumulator columns are its head: dims (ox[0],ox[1],oy[0],oy[1]) of row r0, [2],[3] of row r1
-            const float i0 = rcpf(l0), i1 = rcpf(l1);
-            if (r0ok) *reinterpret_cast<uint2*>(o0) = make_uint2(pack_bf16x2(ox[0] * i0, ox[1] * i0), pack_bf16x2(oy[0] * i0, oy[1] * i0));
-            if (r1ok) *reinterpret_cast<uint2*>(o0 + 128) = make_uint2(pack_bf16x2(ox[2] * i1, ox[3] * i1), pack_bf16x2(oy[2] * i1, oy[3] * i1));
+            const float l0 = d == 3 ? oy[1] : (d == 2 ? oy[0] : ox[1]);
+            const float l1 = d == 3 ? oy[3] : (d == 2 ? oy[2] : ox[3]);
+            if (mine) {   // this lane's accumulator columns are its head: dims (ox[0],ox[1],oy[0],oy[1]) of row r0, [2],[3] of row r1
+                if (!EXACT) bad = wf_l_bad(l0) || wf_l_bad(l1);
+                const float i0 = rcpf(l0), i1 = rcpf(l1);
+                if (r0ok) *reinterpret_cast<uint2*>(o0) = make_uint2(pack_bf16x2(ox[0] * i0, ox[1] * i0), pack_bf16x2(oy[0] * i0, oy[1] * i0));
+                if (r1ok) *reinterpret_cast<uint2*>(o0 + 128) = make_uint2(pack_bf16x2(ox[2] * i1, ox[3] * i1), pack_bf16x2(oy[2] * i1, oy[3] * i1));
+            }
         }
-    }
+        return bad;
+    };
+    if (__any_sync(0xffffffffu, pass(std::false_type{}))) pass(std::true_type{});   // exact pass rewrites the task's O rows
 }
 
 // ---- phase D, 5 <= d <= 7 (16-byte heads): one head per warp pass (k_attn_frag<1, 1, false, 8, ., true>) ---------------
@@ -265,47 +306,78 @@ __device__ __forceinline__ void wf_attn_dp8(const __half* __restrict__ wbase, ui
     const __half* pv = wbase + gq * PH + 2 * HW + 2 * tq;
     const int t6off = gq == 0 ? 48 * PH : 0;
     const int lsrc = (lane & ~3) | ((d & 7) >> 1);   // quad lane that holds column d (the ones column) of the head's d-tile
+    // one pass over the warp's four heads; the fast pass (EXACT = false) streams the key tiles two at a time through
+    // QK^T -> 2^s -> P V and checks the row sums with ONE vote per task (see wf_attn_pack4)
+    auto pass = [&](auto exact) -> bool {
+        constexpr bool EXACT = decltype(exact)::value;
+        bool bad = false;
 #pragma unroll 1
-    for (int hi = 0; hi < 4; hi++) {
-        const int head = sub + 2 * hi;
-        const int uoff = head * 8;
-        uint2 q0 = lds64(pq + uoff), q1 = lds64(pq + q1off + uoff);
-        // k-slots 8..15 of the single k-step hold the NEXT head's columns: zero them on the Q side
-        if (tq >= 2) { q0 = make_uint2(0u, 0u); q1 = make_uint2(0u, 0u); }
-        uint2 kk[7];
-        uint32_t vb[7];
+        for (int hi = 0; hi < 4; hi++) {
+            const int head = sub + 2 * hi;
+            const int uoff = head * 8;
+            uint2 q0 = lds64(pq + uoff), q1 = lds64(pq + q1off + uoff);
+            // k-slots 8..15 of the single k-step hold the NEXT head's columns: zero them on the Q side
+            if (tq >= 2) { q0 = make_uint2(0u, 0u); q1 = make_uint2(0u, 0u); }
+            float o[4];
+            if (EXACT) {
+                float s[7][4];
+                uint32_t vb[7];
 #pragma unroll
-        for (int nt = 0; nt < 7; nt++) {
-            kk[nt] = lds64(pk + (nt < 6 ? nt * 8 * PH : t6off) + uoff);
-            vb[nt] = movm_trans(lds32(pv + (nt < 6 ? nt * 8 * PH : t6off) + uoff));
-        }
-        float o[4];
-        float l0, l1;
-        auto pass = [&](auto exact) {
-            float s[7][4];
+                for (int nt = 0; nt < 7; nt++) {
+                    const uint2 kk = lds64(pk + (nt < 6 ? nt * 8 * PH : t6off) + uoff);
+                    mma16816_cd(s[nt], q0.x, q1.x, q0.y, q1.y, kk.x, kk.y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
+                    vb[nt] = movm_trans(lds32(pv + (nt < 6 ? nt * 8 * PH : t6off) + uoff));
+                }
+                wf_apply_mask(s, m0, m1);
+                uint32_t pf[7][2];
+                wf_softmax_p<true>(s, pf);
+                mma16816_bf16_z(o, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vb[0], vb[1]);
 #pragma unroll
-            for (int nt = 0; nt < 7; nt++)
-                mma16816_cd(s[nt], q0.x, q1.x, q0.y, q1.y, kk[nt].x, kk[nt].y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
-            wf_apply_mask(s, m0, m1);
-            uint32_t pf[7][2];
-            wf_softmax_p<decltype(exact)::value>(s, pf);
-            mma16816_bf16_z(o, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vb[0], vb[1]);
+                for (int j = 1; j < 4; j++) {
+                    const uint32_t a2 = (2 * j + 1 < 7) ? pf[2 * j + 1][0] : 0u, a3 = (2 * j + 1 < 7) ? pf[2 * j + 1][1] : 0u;
+                    mma16816_bf16(o, pf[2 * j][0], pf[2 * j][1], a2, a3, vb[2 * j], (2 * j + 1 < 7) ? vb[2 * j + 1] : 0u);
+                }
+            } else {
 #pragma unroll
-            for (int j = 1; j < 4; j++) {
-                const uint32_t a2 = (2 * j + 1 < 7) ? pf[2 * j + 1][0] : 0u, a3 = (2 * j + 1 < 7) ? pf[2 * j + 1][1] : 0u;
-                mma16816_bf16(o, pf[2 * j][0], pf[2 * j][1], a2, a3, vb[2 * j], (2 * j + 1 < 7) ? vb[2 * j + 1] : 0u);
+                for (int jj = 0; jj < 4; jj++) {   // k-step jj of P V = key tiles 2jj, 2jj + 1
+                    uint32_t pf[2][2], vb[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int nt = 2 * jj + h;
+                        if (nt < 7) {
+                            const uint2 kk = lds64(pk + (nt < 6 ? nt * 8 * PH : t6off) + uoff);
+                            vb[h] = movm_trans(lds32(pv + (nt < 6 ? nt * 8 * PH : t6off) + uoff));
+                            float s[4];
+                            mma16816_cd(s, q0.x, q1.x, q0.y, q1.y, kk.x, kk.y, bias[nt][0], bias[nt][1], bias[nt][2], bias[nt][3]);
+                            if (m0 | m1) {
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    if ((m0 >> (2 * nt + e)) & 1u) s[e] = WF_MASKED;
+                                    if ((m1 >> (2 * nt + e)) & 1u) s[2 + e] = WF_MASKED;
+                                }
+                            }
+                            pf[h][0] = pack_bf16x2(ex2f(s[0]), nt < 6 ? ex2f(s[1]) : 0.f);
+                            pf[h][1] = pack_bf16x2(ex2f(s[2]), nt < 6 ? ex2f(s[3]) : 0.f);
+                        } else {
+                            pf[h][0] = 0u; pf[h][1] = 0u; vb[h] = 0u;
+                        }
+                    }
+                    if (jj == 0) mma16816_bf16_z(o, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vb[0], vb[1]);
+                    else mma16816_bf16(o, pf[0][0], pf[0][1], pf[1][0], pf[1][1], vb[0], vb[1]);
+                }
             }
             // row sums = column d of P V (the ones column): quad lane (d % 8) / 2, element d % 2
             const float c0 = (d & 1) ? o[1] : o[0], c1 = (d & 1) ? o[3] : o[2];
-            l0 = __shfl_sync(0xffffffffu, c0, lsrc); l1 = __shfl_sync(0xffffffffu, c1, lsrc);
-        };
-        pass(std::false_type{});
-        if (__any_sync(0xffffffffu, wf_l_bad(l0) || wf_l_bad(l1))) pass(std::true_type{});
-        const float i0 = rcpf(l0), i1 = rcpf(l1);
-        uint8_t* o0 = sA2 + (uint32_t)head * WF_LBO + (uint32_t)(rowbase + r0) * 16u + (uint32_t)tq * 4u;
-        if (r0ok) *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(o[0] * i0, o[1] * i0);
-        if (r1ok) *reinterpret_cast<uint32_t*>(o0 + 128) = pack_bf16x2(o[2] * i1, o[3] * i1);
-    }
+            const float l0 = __shfl_sync(0xffffffffu, c0, lsrc), l1 = __shfl_sync(0xffffffffu, c1, lsrc);
+            if (!EXACT) bad = bad || wf_l_bad(l0) || wf_l_bad(l1);
+            const float i0 = rcpf(l0), i1 = rcpf(l1);
+            uint8_t* o0 = sA2 + (uint32_t)head * WF_LBO + (uint32_t)(rowbase + r0) * 16u + (uint32_t)tq * 4u;
+            if (r0ok) *reinterpret_cast<uint32_t*>(o0) = pack_bf16x2(o[0] * i0, o[1] * i0);
+            if (r1ok) *reinterpret_cast<uint32_t*>(o0 + 128) = pack_bf16x2(o[2] * i1, o[3] * i1);
+        }
+        return bad;
+    };
+    if (__any_sync(0xffffffffu, pass(std::false_type{}))) pass(std::true_type{});   // exact pass rewrites the task's O rows
 }
 
 // wa_ws.cu: warp-specialised flavour for 8-byte heads (helper warps + attention warps, one CTA per SM)
