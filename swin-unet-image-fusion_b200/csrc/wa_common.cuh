@@ -311,7 +311,7 @@ __device__ __forceinline__ void wf_attn_dp8(const __half* __restrict__ wbase, ui
     auto pass = [&](auto exact) -> bool {
         constexpr bool EXACT = decltype(exact)::value;
         bool bad = false;
-#pragma unroll 1
+#pragma unroll 2
         for (int hi = 0; hi < 4; hi++) {
             const int head = sub + 2 * hi;
             const int uoff = head * 8;

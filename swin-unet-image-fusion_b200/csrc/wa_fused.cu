@@ -203,8 +203,9 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_wa_fused(WaFused p) {
 
         // ---- D: attention core of t_i, window by window ---------------------------------------------------------------------
         if (!(p.debug & 1)) {
-#pragma unroll 1
-            for (int w = 0; w < nw; w++) {
+#pragma unroll
+            for (int w = 0; w < WF_WIN; w++) {
+                if (w >= nw) break;
                 uint32_t m0 = 0, m1 = 0;
                 if (g.shift) {   // boundary windows of the shifted frame are the only ones whose tokens span several regions
                     const uint32_t win = (uint32_t)(t * WF_WIN + w);
