@@ -316,7 +316,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
             }
             ws_helper_bar();   // A1 of tile j complete; every helper has finished iteration j - 1 (F(j-4) released its staging slot)
             if (j < J) {
-                prefetch(j + WS_PD);
                 if (tid == 0) {
                     const uint32_t st = (uint32_t)j & 1u;
                     if (j == 0) mbar_wait(w_full, 0);
@@ -437,6 +436,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
                 }
                 tc_fence_before_sync();
             }
+            // gather of tile j + PD: issued last -- warp 1's address arithmetic for it used to sit between the barrier and its share of
+            // the q|k|v rows, i.e. on the path to qkv_full; the copy itself has two tiles of time.  (Its slot held tile j + PD - RS =
+            // j - 4, scattered in iteration j - 1 by every helper: all of them passed this iteration's barrier since.)
+            if (j < J) prefetch(j + WS_PD);
         }
     } else {
         // =========================== attention warps ===============================================================================
