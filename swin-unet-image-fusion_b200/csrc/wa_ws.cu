@@ -300,6 +300,51 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
         for (int j = 0; j < WS_PD; j++) prefetch(j);
 #pragma unroll 1
         for (int j = 0; j < J + 3; j++) {
+            // Order inside an iteration: C(j-1) comes FIRST.  The attention warps are waiting for exactly these rows (qkv_full), the
+            // accumulator they come from was committed an iteration ago, and nothing of A(j) / B(j) is needed for them -- with C after
+            // the barrier and the MMA issue, the rows arrived ~2,500 cycles later than they could (r2 phase trace).
+            // ---- C(j-1): D1 -> + bias -> fp16 q|k|v rows of the stage the attention warps read next -----------------------------
+            if (j >= 1 && j - 1 < J) {
+                const int jc = j - 1;
+                const uint32_t st = (uint32_t)jc & 1u, par = ((uint32_t)jc >> 1) & 1u;
+                const int nrows = tile_rows(tile_of(jc));
+                mbar_wait_relaxed(&d1_full[st], par);
+                mbar_wait_relaxed(&qkv_empty[st], par ^ 1u);   // rows of tile jc - 2 consumed
+                __syncwarp();
+                tc_fence_after_sync();
+                uint8_t* qrow = smem + L.qkv[st] + (uint32_t)row * PITCH;
+#pragma unroll
+                for (int half = 0; half < ((p.debug & 4) ? 0 : 2); half++) {   // three TMEM loads in flight per wait
+                    uint32_t r[3][16];
+#pragma unroll
+                    for (int u = 0; u < 3; u++) tmem_ld16_issue(tlane + st * WS_D1_STRIDE + (uint32_t)(half * 48 + u * 16), r[u]);
+                    tmem_ld_wait();
+                    if (row < nrows) {
+#pragma unroll
+                        for (int u = 0; u < 3; u++) {
+                            const int c16 = half * 48 + u * 16;
+                            float v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(sbias + c16 + i);
+                                v[i] = __uint_as_float(r[u][i]) + bb.x; v[i + 1] = __uint_as_float(r[u][i + 1]) + bb.y;
+                                v[i + 2] = __uint_as_float(r[u][i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[u][i + 3]) + bb.w;
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(qrow + c16 * 2);
+                            if (c16 < 2 * HW) {   // q, k: fp16
+                                dst[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+                                dst[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+                            } else {              // v: bf16, the B operand of P V with P = 2^s (wf_softmax_p)
+                                dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                                dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                            }
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ws_arrive(&qkv_full[st]);
+            }
             // ---- A(j), B(j): staged rows -> LayerNorm -> A1[j & 1]; q|k|v projection -> D1[j & 1] --------------------------------
             if (j < J) {
                 const int t = tile_of(j);
@@ -345,48 +390,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_wa_ws(WaFused p) {
                     umma_commit(&d1_full[st]);
                 }
                 __syncwarp();
-            }
-            // ---- C(j-1): D1 -> + bias -> fp16 q|k|v rows of the stage the attention warps read next -----------------------------
-            if (j >= 1 && j - 1 < J) {
-                const int jc = j - 1;
-                const uint32_t st = (uint32_t)jc & 1u, par = ((uint32_t)jc >> 1) & 1u;
-                const int nrows = tile_rows(tile_of(jc));
-                mbar_wait_relaxed(&d1_full[st], par);
-                mbar_wait_relaxed(&qkv_empty[st], par ^ 1u);   // rows of tile jc - 2 consumed
-                __syncwarp();
-                tc_fence_after_sync();
-                uint8_t* qrow = smem + L.qkv[st] + (uint32_t)row * PITCH;
-#pragma unroll
-                for (int half = 0; half < ((p.debug & 4) ? 0 : 2); half++) {   // three TMEM loads in flight per wait
-                    uint32_t r[3][16];
-#pragma unroll
-                    for (int u = 0; u < 3; u++) tmem_ld16_issue(tlane + st * WS_D1_STRIDE + (uint32_t)(half * 48 + u * 16), r[u]);
-                    tmem_ld_wait();
-                    if (row < nrows) {
-#pragma unroll
-                        for (int u = 0; u < 3; u++) {
-                            const int c16 = half * 48 + u * 16;
-                            float v[16];
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 bb = *reinterpret_cast<const float4*>(sbias + c16 + i);
-                                v[i] = __uint_as_float(r[u][i]) + bb.x; v[i + 1] = __uint_as_float(r[u][i + 1]) + bb.y;
-                                v[i + 2] = __uint_as_float(r[u][i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[u][i + 3]) + bb.w;
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(qrow + c16 * 2);
-                            if (c16 < 2 * HW) {   // q, k: fp16
-                                dst[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
-                                dst[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
-                            } else {              // v: bf16, the B operand of P V with P = 2^s (wf_softmax_p)
-                                dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                                dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-                            }
-                        }
-                    }
-                }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) ws_arrive(&qkv_full[st]);
             }
             // ---- E(j-2): the attention warps have written O of tile j-2 -> projection on tcgen05 --------------------------------------
             if (j >= 2 && j - 2 < J && tid == 0) {
