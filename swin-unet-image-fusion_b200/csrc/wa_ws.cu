@@ -1,14 +1,15 @@
 // Warp-specialised fused window attention for 8-byte heads (d <= 3, C <= 32: stage 0 of the model, the longest operator of
 // the forward pass).  Same mathematics and the same data path as wa_fused.cu -- gather + LayerNorm -> q|k|v on tcgen05 ->
-// HMMA attention core on fp16 rows in shared memory -> projection on tcgen05 -> + bias + residual, scattered back
+// HMMA attention core on q|k (fp16) / v (bf16) rows in shared memory -> projection on tcgen05 -> + bias + residual, scattered back
 // (a001:448-474 + a004:29-38) -- but the two kinds of work no longer take turns:
 //
 //   warps 0-3   helpers    everything that is latency: bulk-copy gather of the next tiles' rows (two tiles ahead, one copy per
 //                          window row; a tile stays staged until its scatter has taken the residual: x is read once),
 //                          LayerNorm -> A1, tcgen05.mma issue, TMEM -> fp16 q|k|v rows, TMEM -> + b_o + residual -> HBM.
 //                          They run one tile ahead of the attention warps and one to three tiles behind them
-//                          (iteration j: A(j), B(j) | C(j-1) | E(j-2) | F(j-3)), every buffer between the two
-//                          groups (q|k|v rows, A1, A2, both TMEM accumulators) is double buffered.
+//                          (iteration j: C(j-1) | A(j), barrier, B(j) | E(j-2) | F(j-3) | gather of tile j+2 -- the rows the
+//                          attention warps wait for come first, the gather's address arithmetic last), every buffer between
+//                          the two groups (q|k rows fp16 / v rows bf16, A1, A2, both TMEM accumulators) is double buffered.
 //   warps 4-15  attention  the softmax-bound core and nothing else: warp = (window of the tile, 16-row slab 0..2,
 //                          head parity), four heads per pass (wf_attn_pack4).  They never wait for HBM, the tensor
 //                          core or TMEM -- only for the q|k|v rows of the next tile, which the helpers finish while the
