@@ -28,7 +28,7 @@ def reference(s2: torch.Tensor, v: torch.Tensor):
 
 def test_fast_pass_matches_shifted_softmax_inside_the_window():
     g = torch.Generator().manual_seed(0)
-    for scale, offset in [(1.0, 0.0), (8.0, 0.0), (12.0, 40.0), (12.0, -60.0), (3.0, 90.0), (3.0, -85.0)]:
+    for scale, offset in [(1.0, 0.0), (8.0, 0.0), (12.0, 40.0), (12.0, -60.0), (3.0, 80.0), (3.0, -85.0)]:
         s2 = torch.randn(64, 49, generator=g) * scale + offset
         v = torch.randn(49, 3, generator=g)
         o, bad = fast_pass(s2, v)
