@@ -39,7 +39,9 @@ def _worker(rank, world, port, n_buckets, out):
     ((m(x[shard]) - y[shard]) ** 2).sum().backward()
     flat.all_reduce_grads(n_buckets=n_buckets)
     if rank == 0:
-        out.put(flat.flat_grad.clone())
+        # numpy, not a tensor: torch shares tensors between processes by file descriptor, and the receiver must fetch it while
+        # this process is still alive -- a race with the exit below (seen as ConnectionResetError / FileNotFoundError)
+        out.put(flat.flat_grad.detach().numpy().copy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -54,7 +56,7 @@ def test_flat_gradient_allreduce_world2(n_buckets):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_buckets, out)) for r in range(2)]
     for p in procs:
         p.start()
-    got = out.get(timeout=120)
+    got = torch.from_numpy(out.get(timeout=120))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -96,8 +98,8 @@ def _init_worker(rank, world, port, out):
         m[1].running_mean.fill_(float(rank + 1))
         m[1].running_var.fill_(float(rank + 2))
     tr = DataParallelTrainer(m, loss_fn=None)
-    out.put((rank, tr.flat.flat_param.clone(), m[1].running_mean.clone(), m[1].running_var.clone(),
-             [p.detach().clone() for p in m.parameters()]))
+    out.put((rank, tr.flat.flat_param.detach().numpy().copy(), m[1].running_mean.numpy().copy(), m[1].running_var.numpy().copy(),
+             [p.detach().numpy().copy() for p in m.parameters()]))   # by value (see _worker)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -114,7 +116,7 @@ def test_trainer_broadcasts_initial_parameters_and_buffers_world2():
     got = dict()
     for _ in range(2):
         r = out.get(timeout=120)
-        got[r[0]] = r[1:]
+        got[r[0]] = (torch.from_numpy(r[1]), torch.from_numpy(r[2]), torch.from_numpy(r[3]), [torch.from_numpy(a) for a in r[4]])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
