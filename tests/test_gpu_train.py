@@ -339,7 +339,8 @@ def _dp_worker(rank, world, port, out):
         losses = [float(tr.step(ir[sl].cuda(), vis[sl].cuda())) for _ in range(2)]
         torch.cuda.synchronize()
         if rank == 0:
-            out.put((losses, {n: p.detach().cpu() for n, p in _named_unique(m).items()}))
+            # by value (numpy): shared-memory tensors are fetched from this process and race with its exit
+            out.put((losses, {n: p.detach().cpu().numpy().copy() for n, p in _named_unique(m).items()}))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -356,6 +357,7 @@ def test_two_gpu_data_parallel_step_equals_one_gpu_on_the_concatenated_batch():
     for p in procs:
         p.start()
     losses2, params2 = out.get(timeout=600)
+    params2 = {n: torch.from_numpy(a) for n, a in params2.items()}
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0
